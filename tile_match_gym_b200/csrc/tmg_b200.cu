@@ -1,0 +1,304 @@
+// tmg_b200.cu -- host side of the C ABI declared in include/tmg_b200.h (sm_100a only, no CPU fallback).
+#include "tmg_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "tmg_device.cuh"
+
+using namespace tmg;
+
+struct tmg_env {
+    tmg_config cfg;
+    Params p;
+    int L;          // lanes per board: 8, 16 or 32
+    int planes;     // one-hot planes
+    int32_t* actions_dev;  // staging for tmg_step_host
+    void* base;     // one allocation backs every buffer
+    size_t bytes;
+};
+
+namespace {
+
+int vec_width(size_t stride_bytes) {
+    int w = 16;
+    while (w > 1 && (stride_bytes % (size_t)w) != 0) w >>= 1;
+    return w;
+}
+int ptr_vec_width(const void* ptr, int w) {
+    while (w > 1 && (reinterpret_cast<uintptr_t>(ptr) % (uintptr_t)w) != 0) w >>= 1;
+    return w;
+}
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return TMG_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return TMG_ERR_INVALID_ARG;
+    return TMG_OK;
+}
+
+template <typename F> int launch_by_lanes(const tmg_env* e, F&& f) {
+    switch (e->L) {
+        case 8: return f(std::integral_constant<int, 8>());
+        case 16: return f(std::integral_constant<int, 16>());
+        default: return f(std::integral_constant<int, 32>());
+    }
+}
+
+int last_error() { return cudaGetLastError() == cudaSuccess ? TMG_OK : TMG_ERR_CUDA; }
+
+template <int L> int grid_for(int n) { return (n + Cfg<L>::GPB - 1) / Cfg<L>::GPB; }
+
+}  // namespace
+
+extern "C" {
+
+int tmg_abi_version(void) { return TMG_ABI_VERSION; }
+
+const char* tmg_error_string(int code) {
+    switch (code) {
+        case TMG_OK: return "ok";
+        case TMG_ERR_INVALID_ARG: return "invalid argument";
+        case TMG_ERR_UNSUPPORTED_SHAPE: return "unsupported board shape or colour count";
+        case TMG_ERR_CUDA: return "CUDA error";
+        case TMG_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case TMG_ERR_OOM: return "out of device memory";
+        case TMG_ERR_STATE: return "call not valid in this state";
+        default: return "unknown error";
+    }
+}
+
+const char* tmg_status_string(uint32_t status) {
+    static thread_local char buf[256];
+    static const char* names[] = {"bad_action", "needs_reset", "draws_exhausted", "reset_cap",
+                                  "line_overflow", "dfs_overflow", "invalid_board", "internal"};
+    buf[0] = 0;
+    for (int i = 0; i < 8; ++i)
+        if (status & (1u << i)) {
+            if (buf[0]) strncat(buf, "|", sizeof(buf) - strlen(buf) - 1);
+            strncat(buf, names[i], sizeof(buf) - strlen(buf) - 1);
+        }
+    if (!buf[0]) strncpy(buf, "ok", sizeof(buf));
+    return buf;
+}
+
+int tmg_num_actions(int32_t R, int32_t C) { return 2 * R * C - R - C; }
+
+int tmg_onehot_planes(int32_t K, uint32_t specials) {
+    return K + !!(specials & TMG_SP_COOKIE) + !!(specials & TMG_SP_VERTICAL_LASER) +
+           !!(specials & TMG_SP_HORIZONTAL_LASER) + !!(specials & TMG_SP_BOMB);
+}
+
+int tmg_action_to_coords(int32_t R, int32_t C, int32_t a, int32_t out[4]) {
+    if (R < 1 || C < 1 || a < 0 || a >= tmg_num_actions(R, C)) return TMG_ERR_INVALID_ARG;
+    if (a < C * (R - 1)) { out[0] = a / C; out[1] = a % C; out[2] = out[0] + 1; out[3] = out[1]; }
+    else { const int j = a - C * (R - 1); out[0] = j / (C - 1); out[1] = j % (C - 1); out[2] = out[0]; out[3] = out[1] + 1; }
+    return TMG_OK;
+}
+
+int tmg_create(const tmg_config* cfg, tmg_env** out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(tmg_config)) return TMG_ERR_INVALID_ARG;
+    *out = nullptr;
+    const int R = cfg->num_rows, C = cfg->num_cols, K = cfg->num_colours, N = cfg->num_envs;
+    if (N < 1 || cfg->num_moves < 1) return TMG_ERR_INVALID_ARG;
+    if (R < 1 || C < 2 || R > TMG_MAX_ROWS || C > TMG_MAX_COLS || K < 1 || K > TMG_MAX_COLOURS || R * C < 2)
+        return TMG_ERR_UNSUPPORTED_SHAPE;
+    if (cfg->autoreset < 0 || cfg->autoreset > 2 || cfg->refill_mode < 0 || cfg->refill_mode > 1) return TMG_ERR_INVALID_ARG;
+    int rc = check_device(cfg->device);
+    if (rc != TMG_OK) return rc;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return TMG_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return TMG_ERR_CUDA;
+    if (prop.major != 10) return TMG_ERR_NO_DEVICE;  // built for sm_100a only
+
+    tmg_env* e = new (std::nothrow) tmg_env();
+    if (!e) return TMG_ERR_OOM;
+    e->cfg = *cfg;
+    e->L = (C <= 8 && R <= 16) ? 8 : ((C <= 16 && R <= 16) ? 16 : 32);
+    e->planes = tmg_onehot_planes(K, cfg->specials);
+    Params& p = e->p;
+    memset(&p, 0, sizeof(p));
+    p.N = N; p.R = R; p.C = C; p.K = K; p.P = R * C; p.A = tmg_num_actions(R, C);
+    p.num_moves = cfg->num_moves;
+    p.specials = cfg->specials;
+    p.autoreset = cfg->autoreset;
+    p.use_inj = cfg->refill_mode == TMG_REFILL_INJECTED;
+    p.flags = cfg->flags;
+    p.max_iters = cfg->max_reset_iters > 0 ? cfg->max_reset_iters : 16384;
+    p.key0 = (uint32_t)cfg->seed;
+    p.key1 = (uint32_t)(cfg->seed >> 32);
+    p.env_id_offset = cfg->env_id_offset;
+    p.board_vecw = vec_width((size_t)2 * p.P);
+    p.mask_vecw = vec_width((size_t)p.A);
+    p.init_vecw = p.board_vecw;
+
+    // one slab, every array 256-byte aligned
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_board = take((size_t)N * 2 * p.P), o_timer = take((size_t)N * 4), o_dc = take((size_t)N * 8),
+                 o_sc = take((size_t)N * 8), o_rew = take((size_t)N * 4), o_term = take(N), o_comb = take(N),
+                 o_new = take((size_t)N * 4), o_act = take((size_t)N * 4), o_shuf = take(N),
+                 o_mask = take((size_t)N * p.A), o_left = take((size_t)N * 4), o_stat = take((size_t)N * 4),
+                 o_actions = take((size_t)N * 4);
+    e->bytes = off;
+    if (cudaMalloc(&e->base, e->bytes) != cudaSuccess) { cudaGetLastError(); delete e; return TMG_ERR_OOM; }
+    if (cudaMemset(e->base, 0, e->bytes) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
+    char* b = static_cast<char*>(e->base);
+    p.board = reinterpret_cast<int8_t*>(b + o_board);
+    p.timer = reinterpret_cast<int32_t*>(b + o_timer);
+    p.draw_cursor = reinterpret_cast<uint64_t*>(b + o_dc);
+    p.shuffle_cursor = reinterpret_cast<uint64_t*>(b + o_sc);
+    p.reward = reinterpret_cast<int32_t*>(b + o_rew);
+    p.terminated = reinterpret_cast<uint8_t*>(b + o_term);
+    p.is_comb = reinterpret_cast<uint8_t*>(b + o_comb);
+    p.new_specials = reinterpret_cast<int32_t*>(b + o_new);
+    p.activated = reinterpret_cast<int32_t*>(b + o_act);
+    p.shuffled = reinterpret_cast<uint8_t*>(b + o_shuf);
+    p.mask = reinterpret_cast<uint8_t*>(b + o_mask);
+    p.moves_left = reinterpret_cast<int32_t*>(b + o_left);
+    p.status = reinterpret_cast<uint32_t*>(b + o_stat);
+    e->actions_dev = reinterpret_cast<int32_t*>(b + o_actions);
+    // timer = -1: "reset has never been called" (tile_match_env.py:75)
+    if (cudaMemset(p.timer, 0xff, (size_t)N * 4) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
+    if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
+    *out = e;
+    return TMG_OK;
+}
+
+int tmg_destroy(tmg_env* e) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    cudaSetDevice(e->cfg.device);
+    cudaFree(e->base);
+    delete e;
+    return TMG_OK;
+}
+
+int tmg_get_buffers(tmg_env* e, tmg_buffers* out) {
+    if (!e || !out) return TMG_ERR_INVALID_ARG;
+    const Params& p = e->p;
+    out->board = p.board; out->timer = p.timer; out->draw_cursor = p.draw_cursor; out->shuffle_cursor = p.shuffle_cursor;
+    out->reward = p.reward; out->terminated = p.terminated; out->is_combination_match = p.is_comb;
+    out->num_new_specials = p.new_specials; out->num_specials_activated = p.activated; out->shuffled = p.shuffled;
+    out->mask = p.mask; out->num_moves_left = p.moves_left; out->status = p.status;
+    return TMG_OK;
+}
+
+int tmg_set_injected_draws(tmg_env* e, const uint8_t* draws_dev, int64_t per_env_len) {
+    if (!e || per_env_len < 0 || (!draws_dev && per_env_len > 0)) return TMG_ERR_INVALID_ARG;
+    if (!e->p.use_inj) return TMG_ERR_STATE;
+    e->p.inj = draws_dev;
+    e->p.inj_len = per_env_len;
+    return TMG_OK;
+}
+
+int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boards_dev, void* stream) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    Params p = e->p;
+    p.reset_mask = reset_mask_dev;
+    p.init_boards = init_boards_dev;
+    p.init_vecw = init_boards_dev ? ptr_vec_width(init_boards_dev, p.board_vecw) : p.board_vecw;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return launch_by_lanes(e, [&](auto lanes) {
+        constexpr int L = decltype(lanes)::value;
+        k_reset<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        return last_error();
+    });
+}
+
+int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
+    if (!e || !actions_dev) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    Params p = e->p;
+    p.actions = actions_dev;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return launch_by_lanes(e, [&](auto lanes) {
+        constexpr int L = decltype(lanes)::value;
+        k_step<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        return last_error();
+    });
+}
+
+int tmg_legal_mask(tmg_env* e, void* stream) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    const Params p = e->p;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return launch_by_lanes(e, [&](auto lanes) {
+        constexpr int L = decltype(lanes)::value;
+        k_mask<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        return last_error();
+    });
+}
+
+static int onehot_launch(tmg_env* e, void* out, bool f32, void* stream) {
+    if (!e || !out) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    const Params p = e->p;
+    const long long total = (long long)p.N * e->planes * p.P;
+    const long long threads = (total + 3) / 4;
+    const int block = 256;
+    const long long grid = (threads + block - 1) / block;
+    if (grid > 0x7fffffffLL) return TMG_ERR_INVALID_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (f32) k_onehot<float><<<(unsigned)grid, block, 0, st>>>(p, static_cast<float*>(out), e->planes);
+    else k_onehot<uint8_t><<<(unsigned)grid, block, 0, st>>>(p, static_cast<uint8_t*>(out), e->planes);
+    return last_error();
+}
+int tmg_encode_onehot(tmg_env* e, uint8_t* out_dev, void* stream) { return onehot_launch(e, out_dev, false, stream); }
+int tmg_encode_onehot_f32(tmg_env* e, float* out_dev, void* stream) { return onehot_launch(e, out_dev, true, stream); }
+
+int tmg_clear_status(tmg_env* e, void* stream) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    k_clear_status<<<(e->p.N + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(e->p.status, e->p.N);
+    return last_error();
+}
+
+int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
+    if (!e || !io || !io->actions) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Params& p = e->p;
+    const size_t N = (size_t)p.N;
+    if (cudaMemcpyAsync(e->actions_dev, io->actions, N * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return TMG_ERR_CUDA;
+    const int rc = tmg_step(e, e->actions_dev, stream);
+    if (rc != TMG_OK) return rc;
+    bool ok = true;
+    auto back = [&](void* dst, const void* src, size_t bytes) {
+        if (dst) ok &= cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    };
+    back(io->board, p.board, N * 2 * p.P);
+    back(io->reward, p.reward, N * 4);
+    back(io->terminated, p.terminated, N);
+    back(io->mask, p.mask, N * p.A);
+    back(io->num_moves_left, p.moves_left, N * 4);
+    back(io->is_combination_match, p.is_comb, N);
+    back(io->num_new_specials, p.new_specials, N * 4);
+    back(io->num_specials_activated, p.activated, N * 4);
+    back(io->shuffled, p.shuffled, N);
+    back(io->status, p.status, N * 4);
+    if (!ok) return TMG_ERR_CUDA;
+    return cudaStreamSynchronize(st) == cudaSuccess ? TMG_OK : TMG_ERR_CUDA;
+}
+
+int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) {
+    if (!e || op < TMG_OP_GRAVITY || op > TMG_OP_COUNT_LINES) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    Params p = e->p;
+    p.dbg_op = op;
+    p.dbg_args = args_dev;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return launch_by_lanes(e, [&](auto lanes) {
+        constexpr int L = decltype(lanes)::value;
+        k_debug<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        return last_error();
+    });
+}
+
+}  // extern "C"

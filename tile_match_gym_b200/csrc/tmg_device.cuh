@@ -1,0 +1,1275 @@
+// tmg_device.cuh -- device side of the B200 tile-match engine (sm_100a).
+//
+// One sub-warp ("group") of L lanes owns one board; lane c owns column c.  The board's colour and type
+// planes live in shared memory in exactly the HBM layout ([2][R][C] int8), loaded/stored with the widest
+// vector the env stride allows.  Parallel parts (line scan by ballot, gravity by per-lane compaction,
+// refill ranks by ballot/popc + counter-based Philox, legal-move mask by per-colour row bitboards and
+// shuffles) run on all lanes; the order-dependent list semantics of the reference (line classification,
+// bomb merging, creation cells, the activation DFS, combination matches) run on the group's leader lane
+// over small shared-memory tables.  The whole cascade loop stays inside the kernel.
+//
+// Reference being restated (never copied): /root/reference/src/tile_match_gym/board.py -- cited per
+// function as "ref :NNN".  Semantics are literal for every FULL board whose cells are arbitrary
+// (colour, type) pairs, so states the reference can reach through its shuffle/redraw path (e.g. a cookie
+// that was given a colour by remove_colour_lines, ref :129) behave identically.
+//
+// This header is also compiled by tests/emu (a CPU lane emulator used only by the test-suite to debug
+// kernel logic without a GPU); TMG_EMU selects the shim.  The product never builds with TMG_EMU.
+#pragma once
+#include <stdint.h>
+
+#ifdef TMG_EMU
+#include "emu_shim.h"
+// the emulator checks that all lanes of a group are at the same collective (source line of the caller)
+#define TMG_SITE_P0 int site_ = __builtin_LINE()
+#define TMG_SITE_P , int site_ = __builtin_LINE()
+#define TMG_SITE_SET emu::site_id = site_;
+#else
+#include <cuda_runtime.h>
+#define TMG_SITE_P0
+#define TMG_SITE_P
+#define TMG_SITE_SET
+#endif
+
+namespace tmg {
+
+// ---- status / config constants (values mirror include/tmg_b200.h) ---------------------------------
+enum : uint32_t {
+    ST_BAD_ACTION = 1u, ST_NEEDS_RESET = 2u, ST_DRAWS_EXHAUSTED = 4u, ST_RESET_CAP = 8u,
+    ST_LINE_OVERFLOW = 16u, ST_DFS_OVERFLOW = 32u, ST_INVALID_BOARD = 64u, ST_INTERNAL = 128u
+};
+enum : uint32_t { SP_COOKIE = 1u, SP_VLASER = 2u, SP_HLASER = 4u, SP_BOMB = 8u };
+enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 };
+enum : uint32_t { FLAG_NO_MASK = 1u };
+enum { OP_GRAVITY = 1, OP_REFILL, OP_RESOLVE_ROUND, OP_ACTIVATE, OP_COMBINE, OP_MOVE, OP_EFFECTIVE, OP_GENERATE,
+       OP_SHUFFLE, OP_COUNT_LINES };
+enum { NAME_NORMAL = 0, NAME_VLASER = 2, NAME_HLASER = 3, NAME_BOMB = 4, NAME_COOKIE = -1 };  // = created tile type
+
+struct Params {
+    int N, R, C, K, P, A, num_moves;
+    uint32_t specials;
+    int autoreset, use_inj;
+    uint32_t flags;
+    int max_iters;
+    uint32_t key0, key1;
+    uint64_t env_id_offset;
+    int board_vecw, mask_vecw, init_vecw;  // widest power-of-two vector (bytes) dividing the per-env strides / pointers
+    // state / outputs (device)
+    int8_t* board;
+    int32_t* timer;
+    uint64_t* draw_cursor;
+    uint64_t* shuffle_cursor;
+    int32_t* reward;
+    uint8_t* terminated;
+    uint8_t* is_comb;
+    int32_t* new_specials;
+    int32_t* activated;
+    uint8_t* shuffled;
+    uint8_t* mask;
+    int32_t* moves_left;
+    uint32_t* status;
+    const uint8_t* inj;
+    long long inj_len;
+    // per-call inputs
+    const int32_t* actions;
+    const uint8_t* reset_mask;
+    const int8_t* init_boards;
+    const int32_t* dbg_args;
+    int dbg_op;
+};
+
+template <int L> struct Cfg {
+    static constexpr int MAXR = (L == 32) ? 32 : 16;
+    static constexpr int MAXP = MAXR * L;
+    static constexpr int ML = 2 * L;                      // line-table capacity per cascade round
+    static constexpr int MLEN = (L > MAXR) ? L : MAXR;    // longest straight line
+    static constexpr int DFS = 4 * L;                     // activation stack depth
+    static constexpr int NW = 4 * (L - 1);                // stream words produced per Philox pass
+    static constexpr unsigned LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);
+    static constexpr int THREADS = 128;
+    static constexpr int GPB = THREADS / L;               // groups (boards) per block
+};
+
+template <int L> struct __align__(16) GroupSmem {
+    int8_t board[2 * Cfg<L>::MAXP];  // colour plane [0,P), type plane [P,2P) -- the HBM layout
+    uint8_t mask[2 * Cfg<L>::MAXP];  // legal-move mask staging (A < 2P)
+    uint32_t wbuf[4 * L];            // stream words of the current Philox pass
+    uint32_t stack[Cfg<L>::DFS];     // activation DFS frames
+    uint32_t line_key[Cfg<L>::ML];   // (top row << 12) | list position  -> processing order
+    uint16_t line_cells[Cfg<L>::ML][Cfg<L>::MLEN];
+    uint16_t match[Cfg<L>::MLEN + 4];
+    uint16_t cq_pos[Cfg<L>::ML];     // special-creation queue (ref :411)
+    uint16_t taken[Cfg<L>::ML];
+    uint16_t cnt[32];                // colour histogram for the cookie (ref :536)
+    uint8_t line_len[Cfg<L>::ML];
+    uint8_t line_colour[Cfg<L>::ML];
+    uint8_t order[Cfg<L>::ML];
+    int8_t cq_type[Cfg<L>::ML];
+    uint8_t cq_colour[Cfg<L>::ML];
+};
+
+// ---- Philox4x32-10 (Random123) ---------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ bool not01(int t) { return t != 0 && t != 1; }
+
+// ---- vector copies between global and the group's shared memory -------------------------------------
+template <int L, typename V> __device__ __forceinline__ void copy_vec(void* dst, const void* src, int nbytes, int lane) {
+    const int n = nbytes / (int)sizeof(V);
+    V* d = reinterpret_cast<V*>(dst);
+    const V* s = reinterpret_cast<const V*>(src);
+    for (int i = lane; i < n; i += L) d[i] = s[i];
+}
+template <int L> __device__ __forceinline__ void copy_bytes(void* dst, const void* src, int nbytes, int vecw, int lane) {
+    switch (vecw) {
+        case 16: copy_vec<L, uint4>(dst, src, nbytes, lane); break;
+        case 8: copy_vec<L, uint2>(dst, src, nbytes, lane); break;
+        case 4: copy_vec<L, uint32_t>(dst, src, nbytes, lane); break;
+        case 2: copy_vec<L, uint16_t>(dst, src, nbytes, lane); break;
+        default: copy_vec<L, uint8_t>(dst, src, nbytes, lane); break;
+    }
+}
+template <int L> __device__ __forceinline__ void zero_bytes(void* dst, int nbytes, int vecw, int lane) {
+    if (vecw >= 4) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        for (int i = lane; i < nbytes / 4; i += L) d[i] = 0u;
+    } else {
+        uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+        for (int i = lane; i < nbytes; i += L) d[i] = 0;
+    }
+}
+
+// ======================================================================================================
+// One board owned by a group of L lanes
+// ======================================================================================================
+template <int L> struct Board {
+    typedef Cfg<L> CF;
+    GroupSmem<L>& s;
+    const Params& p;
+    const int lane;
+    const unsigned gmask;
+    const int gshift;
+    const int env;
+    const int R, C, P, K;
+    int8_t* const col;
+    int8_t* const typ;
+    uint64_t dcur, scur;
+    const uint32_t gid;
+    uint32_t status;
+    int n_new, n_act;  // counters, meaningful on the leader lane (ref :343-344)
+    int nzc;           // leader: number of cells with colour != 0 while a serial section runs; -1 = unknown
+
+    __device__ Board(GroupSmem<L>& sm, const Params& pp, int lane_, unsigned gmask_, int gshift_, int env_)
+        : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(pp.R), C(pp.C), P(pp.P), K(pp.K),
+          col(sm.board), typ(sm.board + pp.P), dcur(0), scur(0), gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)),
+          status(0), n_new(0), n_act(0), nzc(-1) {}
+
+    // ---- group collectives ---------------------------------------------------------------------------
+    __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
+    __device__ __forceinline__ void sync(TMG_SITE_P0) const { TMG_SITE_SET __syncwarp(gmask); }
+    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, src, L); }
+    __device__ __forceinline__ unsigned shflu(unsigned v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, src, L); }
+    __device__ __forceinline__ int radd(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_add_sync(gmask, v); }
+    __device__ __forceinline__ int rmax(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_max_sync(gmask, v); }
+    __device__ __forceinline__ int rmin(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_min_sync(gmask, v); }
+    __device__ __forceinline__ unsigned ror(unsigned v TMG_SITE_P) const { TMG_SITE_SET return __reduce_or_sync(gmask, v); }
+    __device__ __forceinline__ unsigned lt_mask() const { return (1u << lane) - 1u; }
+    // neighbour-lane bitboards: value of lane+d / lane-d, 0 outside [0,L)
+    __device__ __forceinline__ unsigned from_right(unsigned v, int d TMG_SITE_P) const {
+        TMG_SITE_SET
+        const unsigned r = __shfl_down_sync(gmask, v, d, L);
+        return (lane + d < L) ? r : 0u;
+    }
+    __device__ __forceinline__ unsigned from_left(unsigned v, int d TMG_SITE_P) const {
+        TMG_SITE_SET
+        const unsigned r = __shfl_up_sync(gmask, v, d, L);
+        return (lane - d >= 0) ? r : 0u;
+    }
+
+    // ---- state I/O -----------------------------------------------------------------------------------
+    __device__ __forceinline__ void load_board(const int8_t* src, int vecw) {
+        copy_bytes<L>(s.board, src + (size_t)env * 2 * P, 2 * P, vecw, lane);
+        sync();
+    }
+    __device__ __forceinline__ void store_board() {
+        sync();
+        copy_bytes<L>(p.board + (size_t)env * 2 * P, s.board, 2 * P, p.board_vecw, lane);
+    }
+    __device__ __forceinline__ void store_mask() {
+        sync();
+        copy_bytes<L>(p.mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
+    }
+    __device__ __forceinline__ void store_zero_mask() { zero_bytes<L>(p.mask + (size_t)env * p.A, p.A, p.mask_vecw, lane); }
+    __device__ __forceinline__ void load_cursors() { dcur = p.draw_cursor[env]; scur = p.shuffle_cursor[env]; }
+    __device__ __forceinline__ void store_cursors() {
+        if (lane == 0) { p.draw_cursor[env] = dcur; p.shuffle_cursor[env] = scur; }
+    }
+
+    // ---- draw stream -----------------------------------------------------------------------------------
+    // words [start, start+n) of stream `stream` -> s.wbuf[0..n), n <= NW.  All lanes call.
+    __device__ __forceinline__ void fill_words(uint32_t stream, uint64_t start, int n) {
+        const uint64_t b0 = start >> 2;
+        const int nb = (int)(((start + (uint64_t)n - 1) >> 2) - b0) + 1;  // <= L because n <= 4(L-1)
+        if (lane < nb) {
+            const uint64_t b = b0 + (uint64_t)lane;
+            uint32_t w[4];
+            philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, stream, p.key0, p.key1, w);
+            const int base = (int)((long long)(b << 2) - (long long)start);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = base + i;
+                if (idx >= 0 && idx < n) s.wbuf[idx] = w[i];
+            }
+        }
+        sync();
+    }
+    // colour of draw number `k` (relative to dcur) whose word sits at s.wbuf[widx]  (ref :97,129,239)
+    __device__ __forceinline__ int draw_colour(int k, int widx) {
+        if (p.use_inj) {
+            const long long q = (long long)dcur + k;
+            if (q < p.inj_len) return p.inj[(size_t)env * (size_t)p.inj_len + (size_t)q];
+            status |= ST_DRAWS_EXHAUSTED;
+            return 1;
+        }
+        return 1 + (int)__umulhi(s.wbuf[widx], (uint32_t)K);
+    }
+    // cells [0, n) in row-major order <- next n draws (initial fill ref :97 / row-block redraw ref :129)
+    __device__ void draw_cells(int n, bool set_type) {
+        sync();
+        for (int ps = 0; ps < n; ps += CF::NW) {
+            const int nw = min(CF::NW, n - ps);
+            if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
+            for (int i = lane; i < nw; i += L) {
+                col[ps + i] = (int8_t)draw_colour(ps + i, i);
+                if (set_type) typ[ps + i] = 1;
+            }
+            sync();
+        }
+        dcur += (uint64_t)n;
+    }
+
+    // ---- gravity (ref :217-229) + count of type==0 cells (ref :362,374) ------------------------------------
+    // returns the number of empty cells now on top of this lane's column; *elim gets P - count_nonzero(type)
+    __device__ int gravity(int* elim) {
+        sync();
+        int e = 0, nz = 0;
+        if (lane < C) {
+            int w = R - 1;
+            for (int r = R - 1; r >= 0; --r) {
+                const int i = r * C + lane;
+                const int x = col[i], t = typ[i];
+                nz += (t == 0);
+                if (x != 0 || t != 0) {
+                    if (w != r) { col[w * C + lane] = (int8_t)x; typ[w * C + lane] = (int8_t)t; }
+                    --w;
+                }
+            }
+            e = w + 1;
+            for (; w >= 0; --w) { col[w * C + lane] = 0; typ[w * C + lane] = 0; }
+        }
+        if (elim) *elim = radd(nz);
+        return e;
+    }
+
+    // ---- refill (ref :231-241): the k-th draw goes to the k-th empty cell in row-major order ---------------
+    __device__ void refill(int e) {
+        const int maxe = rmax(e);
+        if (maxe == 0) return;  // ref :238: no rng call when nothing is empty
+        const int total = radd(e);
+        const unsigned lt = lt_mask();
+        for (int ps = 0; ps < total; ps += CF::NW) {
+            const int nw = min(CF::NW, total - ps);
+            if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
+            int base = 0;
+            for (int r = 0; r < maxe; ++r) {
+                const unsigned m = ballot(e > r);
+                if (e > r) {
+                    const int rank = base + __popc(m & lt);
+                    if (rank >= ps && rank < ps + nw) {
+                        col[r * C + lane] = (int8_t)draw_colour(rank, rank - ps);
+                        typ[r * C + lane] = 1;
+                    }
+                }
+                base += __popc(m);
+            }
+            sync();
+        }
+        dcur += (uint64_t)total;
+    }
+
+    // ---- bottom-most line row (ref :158-193) -------------------------------------------------------------
+    struct Scan {
+        int rstar;        // row of the bottom-most anchored lines, -1 if the board has none
+        unsigned mv;      // lanes with a vertical line whose anchor (bottom) is at rstar
+        unsigned hs;      // start columns of the horizontal lines in row rstar
+        unsigned hcells;  // all cells of those horizontal lines
+        unsigned m;       // bit c: colour(rstar,c) == colour(rstar,c+1)
+        int vtop;         // per lane: top row of its vertical line
+        bool has_v;
+    };
+    __device__ Scan scan_lines(int from) {
+        Scan o;
+        o.rstar = -1; o.mv = o.hs = o.hcells = o.m = 0u; o.vtop = 0; o.has_v = false;
+        const bool in = lane < C;
+        for (int r = from; r >= 0; --r) {
+            int x = -1, t = 0, xr = -2;
+            bool v = false;
+            if (in) {
+                const int i = r * C + lane;
+                x = col[i];
+                t = typ[i];
+                if (lane + 1 < C) xr = col[i + 1];
+                if (r >= 2 && t > 0) v = (x == col[i - C]) && (x == col[i - 2 * C]);  // ref :163-173, anchor type only
+            }
+            const unsigned m = ballot(x == xr);
+            const unsigned T = ballot(t > 0);
+            const unsigned mv = ballot(v);
+            unsigned cand = m & (m >> 1) & T;  // anchors of horizontal triples with type > 0 (ref :179-181)
+            unsigned hs = 0u, hcells = 0u;
+            while (cand) {  // left to right; cells of a found line cannot anchor another (ref :179,192)
+                const int sidx = __ffs((int)cand) - 1;
+                const int run = __ffs((int)~(m >> sidx)) - 1;  // line = sidx .. sidx+run
+                const unsigned cells = ((2u << run) - 1u) << sidx;
+                hs |= 1u << sidx;
+                hcells |= cells;
+                cand &= ~cells;
+            }
+            if (mv | hs) {
+                o.rstar = r; o.mv = mv; o.hs = hs; o.hcells = hcells; o.m = m; o.has_v = v;
+                if (v) {
+                    int top = r - 2;
+                    while (top > 0 && col[(top - 1) * C + lane] == x) --top;  // ref :168-172
+                    o.vtop = top;
+                }
+                break;
+            }
+        }
+        return o;
+    }
+    // row of l[0][0] for the first line of get_colour_lines() (ref :127-128)
+    __device__ __forceinline__ int first_line_top(const Scan& sc) {
+        const int cv = sc.mv ? __ffs((int)sc.mv) - 1 : 64;
+        const int ch = sc.hs ? __ffs((int)sc.hs) - 1 : 64;
+        const int vt = shfl(sc.vtop, cv < 64 ? cv : 0);
+        return (cv <= ch) ? vt : sc.rstar;  // vertical is listed before horizontal at the same column (ref :163,179)
+    }
+
+    // ---- line table in the reference's list order (ref :149-215, closed form in SURVEY.md A.4) -------------
+    // returns the number of lines; s.order holds them sorted for process_colour_lines (ref :282)
+    __device__ int build_line_table(const Scan& sc) {
+        const int rs = sc.rstar;
+        const unsigned lt = lt_mask();
+        // phase 1: by column, vertical before horizontal
+        const int before = __popc(sc.mv & lt) + __popc(sc.hs & lt);
+        int n = __popc(sc.mv) + __popc(sc.hs);
+        if (sc.has_v) {
+            const int slot = before;
+            if (slot < CF::ML) {
+                const int len = rs - sc.vtop + 1;
+                for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)((sc.vtop + k) * C + lane);
+                s.line_len[slot] = (uint8_t)len;
+                s.line_colour[slot] = (uint8_t)col[rs * C + lane];
+                s.line_key[slot] = ((uint32_t)sc.vtop << 12) | (uint32_t)slot;
+            }
+        }
+        if ((sc.hs >> lane) & 1u) {
+            const int slot = before + (sc.has_v ? 1 : 0);
+            if (slot < CF::ML) {
+                const int run = __ffs((int)~(sc.m >> lane)) - 1;
+                for (int k = 0; k <= run; ++k) s.line_cells[slot][k] = (uint16_t)(rs * C + lane + k);
+                s.line_len[slot] = (uint8_t)(run + 1);
+                s.line_colour[slot] = (uint8_t)col[rs * C + lane];
+                s.line_key[slot] = ((uint32_t)rs << 12) | (uint32_t)slot;
+            }
+        }
+        // phase 2 (ref :198-214): horizontal segments through the cells of the vertical lines, cut at phase-1 cells
+        if (sc.mv) {
+            const int rmin_ = rmin(sc.has_v ? sc.vtop : 1 << 20);
+            for (int r = rmin_; r <= rs; ++r) {
+                int x = -1, t = 0, xr = -2;
+                if (lane < C) {
+                    x = col[r * C + lane];
+                    t = typ[r * C + lane];
+                    if (lane + 1 < C) xr = col[r * C + lane + 1];
+                }
+                const unsigned m = ballot(x == xr);
+                const unsigned T = ballot(t > 0);
+                const bool origin = sc.has_v && sc.vtop <= r;
+                unsigned Q = ballot(origin);
+                if (r == rs) Q |= sc.hcells;
+                const unsigned pass = T & ~Q;
+                int left = 0, right = 0;
+                bool seg = false;
+                if (origin && t > 0) {  // match_color needs type > 0 on both cells (ref :199)
+                    const unsigned chain_r = (m << 1) & pass;  // bit j: cell j equals cell j-1 and may be entered
+                    const unsigned chain_l = m & pass;         // bit j: cell j equals cell j+1 and may be entered
+                    if (lane + 1 < L) right = __ffs((int)~(chain_r >> (lane + 1))) - 1;
+                    if (lane > 0) left = __clz((int)~(chain_l << (32 - lane)));
+                    seg = (1 + left + right) >= 3;
+                }
+                const unsigned segm = ballot(seg);
+                if (seg) {
+                    const int slot = n + __popc(segm & lt);
+                    if (slot < CF::ML) {
+                        const int len = 1 + left + right;
+                        for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)(r * C + lane - left + k);
+                        s.line_len[slot] = (uint8_t)len;
+                        s.line_colour[slot] = (uint8_t)x;
+                        // same top row: phase 1 first, then phase 2 by (column of the vertical line, row)
+                        s.line_key[slot] = ((uint32_t)r << 12) | (uint32_t)(1024 + lane * 32 + r);
+                    }
+                }
+                n += __popc(segm);
+            }
+        }
+        if (n > CF::ML) { status |= ST_LINE_OVERFLOW; n = CF::ML; }
+        sync();
+        return n;
+    }
+
+    // ===================================================================================================
+    // Serial (leader-lane) part: exact list semantics
+    // ===================================================================================================
+    __device__ __forceinline__ void del_cell(int i) {
+        if (nzc >= 0 && col[i] != 0) --nzc;
+        col[i] = 0;
+        typ[i] = 0;
+    }
+    __device__ void count_nzc() {
+        int n = 0;
+        for (int i = 0; i < P; ++i) n += (col[i] != 0);
+        nzc = n;
+    }
+
+    // frame: kind(2) | cell(10) << 2 | cursor(11) << 12 | colour(5) << 23
+    __device__ __forceinline__ static uint32_t frame(int kind, int cell, int cursor, int mc) {
+        return (uint32_t)kind | ((uint32_t)cell << 2) | ((uint32_t)cursor << 12) | ((uint32_t)mc << 23);
+    }
+    // entry of activate_special (ref :473-499 + the set-up of the cookie branch :530-544); pushes a frame
+    __device__ void enter_activation(int cell, int t, bool counted, int& sp) {
+        if (nzc < 0) count_nzc();
+        if (nzc == 0) return;                      // ref :488-489
+        if (t == 0 || t == 1) { status |= ST_INTERNAL; return; }  // ref :491-492 raises
+        del_cell(cell);                            // ref :496
+        if (counted) ++n_act;                      // ref :498-499
+        int kind, mc = 0;
+        if (t == 2) kind = 0;
+        else if (t == 3) kind = 1;
+        else if (t == 4) kind = 2;
+        else if (t == -1) {
+            kind = 3;
+            if (nzc == 0) return;                  // ref :532-534
+            for (int k = 0; k <= K && k < 32; ++k) s.cnt[k] = 0;
+            for (int i = 0; i < P; ++i) { const int x = col[i]; if (x > 0 && x < 32) ++s.cnt[x]; }
+            int best = 0;
+            for (int k = 1; k <= K && k < 32; ++k) if (s.cnt[k] > best) { best = s.cnt[k]; mc = k; }  // ref :536-537
+            for (int i = 0; i < P; ++i) if (col[i] == mc && typ[i] == 1) del_cell(i);                 // ref :540-544
+        } else { status |= ST_INTERNAL; return; }  // ref :555-556 raises
+        if (sp >= CF::DFS) { status |= ST_DFS_OVERFLOW; return; }
+        s.stack[sp++] = frame(kind, cell, 0, mc);
+    }
+    // activate_special (ref :473-556) as an explicit-stack DFS that re-reads live cells in the reference's order
+    __device__ void activate(int cell0, int t0, bool counted) {
+        int sp = 0;
+        enter_activation(cell0, t0, counted, sp);
+        while (sp > 0) {
+            const uint32_t f = s.stack[sp - 1];
+            const int kind = (int)(f & 3u), cell = (int)((f >> 2) & 1023u), mc = (int)(f >> 23);
+            int cur = (int)((f >> 12) & 2047u);
+            const int r0 = cell / C, c0 = cell - r0 * C;
+            int target = -1;
+            if (kind == 0) {                        // vertical laser: rows top to bottom (ref :502-507)
+                if (cur < R) target = cur * C + c0;
+                ++cur;
+            } else if (kind == 1) {                 // horizontal laser: columns left to right (ref :510-515)
+                if (cur < C) target = r0 * C + cur;
+                ++cur;
+            } else if (kind == 2) {                 // bomb: clipped 3x3, row-major (ref :517-528)
+                const int min_r = max(r0 - 1, 0), max_r = min(r0 + 1, R - 1);
+                const int min_c = max(c0 - 1, 0), max_c = min(c0 + 1, C - 1);
+                const int w = max_c - min_c + 1;
+                if (cur < w * (max_r - min_r + 1)) target = (min_r + cur / w) * C + min_c + cur % w;
+                ++cur;
+            } else {                                // cookie: specials of the chosen colour, row-major (ref :547-554)
+                while (cur < P && !(col[cur] == mc && typ[cur] > 1)) ++cur;
+                if (cur < P) target = cur;
+                ++cur;
+            }
+            if (target < 0) { --sp; continue; }
+            s.stack[sp - 1] = frame(kind, cell, cur, mc);
+            const int t = typ[target];
+            if (not01(t)) enter_activation(target, t, true, sp);  // nested calls always count (ref :505,513,526,554)
+            else if (kind != 3) del_cell(target);
+        }
+    }
+
+    // get_special_creation_pos (ref :429-458) on s.match[0..n)
+    __device__ int creation_pos(int n, int ntaken, bool straight) {
+        auto is_taken = [&](int cell) {
+            for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
+            return false;
+        };
+        int nv = 0;
+        for (int k = 0; k < n; ++k) nv += !is_taken(s.match[k]);
+        if (nv == 0) { status |= ST_INTERNAL; return -1; }  // reference: IndexError
+        if (!straight) {                                    // ref :441-450
+            int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
+            for (int k = 0; k < n; ++k) {                   // max(xs, key=xs.count): first element with the top count
+                const int rr = s.match[k] / C, cc = s.match[k] % C;
+                int nr = 0, nc = 0;
+                for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
+                if (nr > best_rc) { best_rc = nr; best_r = rr; }
+                if (nc > best_cc) { best_cc = nc; best_c = cc; }
+            }
+            const int corner = best_r * C + best_c;
+            int best = -1, bestd = 0;
+            for (int k = 0; k < n; ++k) {
+                const int cell = s.match[k];
+                if (is_taken(cell)) continue;
+                if (cell == corner) return corner;          // ref :446-447
+                const int dr = cell / C - best_r, dc = cell % C - best_c, d = dr * dr + dc * dc;
+                if (best < 0 || d < bestd) { best = cell; bestd = d; }  // stable: first minimum (ref :449)
+            }
+            return best;
+        }
+        // straight: the match is already sorted by (row, col); pick the middle of the valid cells (ref :453-458)
+        const int want = (nv % 2 == 0) ? nv / 2 - 1 : nv / 2;
+        int seen = 0;
+        for (int k = 0; k < n; ++k) {
+            if (is_taken(s.match[k])) continue;
+            if (seen == want) return s.match[k];
+            ++seen;
+        }
+        return -1;
+    }
+
+    // process_colour_lines (ref :269-327) fused with resolve_colour_matches (ref :397-427): the creation cell
+    // of a match depends only on coordinates, so each match is resolved as soon as it is classified; the new
+    // specials are written after all deletions, as in the reference.
+    __device__ void process_and_resolve(int n) {
+        // ref :282: stable sort by the first cell's row == sort by key (keys are unique)
+        for (int i = 0; i < n; ++i) s.order[i] = (uint8_t)i;
+        for (int i = 1; i < n; ++i) {
+            const uint8_t v = s.order[i];
+            const uint32_t kv = s.line_key[v];
+            int j = i - 1;
+            while (j >= 0 && s.line_key[s.order[j]] > kv) { s.order[j + 1] = s.order[j]; --j; }
+            s.order[j + 1] = v;
+        }
+        int qh = 0, qn = n, nslots = n, ncq = 0, ntaken = 0;
+        const bool sp_cookie = p.specials & SP_COOKIE, sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER,
+                   sp_bomb = p.specials & SP_BOMB;
+        while (qh < qn) {
+            const int li = s.order[qh++];                    // ref :285 pop(0)
+            const int len = s.line_len[li];
+            const uint16_t* cells = s.line_cells[li];
+            int mlen = 0, name = NAME_NORMAL, colour = s.line_colour[li];
+            bool have = false;
+            if (len >= 5 && sp_cookie) {                     // ref :287-292
+                for (int k = 0; k < 5; ++k) s.match[mlen++] = cells[k];
+                name = NAME_COOKIE; colour = 0; have = true;
+                if (len - 5 > 2) {
+                    if (nslots < CF::ML && qn < CF::ML) {
+                        const int ns = nslots++;
+                        for (int k = 5; k < len; ++k) s.line_cells[ns][k - 5] = cells[k];
+                        s.line_len[ns] = (uint8_t)(len - 5);
+                        s.line_colour[ns] = s.line_colour[li];
+                        s.order[qn++] = (uint8_t)ns;
+                    } else status |= ST_LINE_OVERFLOW;
+                }
+            } else if (len == 4) {                           // ref :294-302
+                for (int k = 0; k < 4; ++k) s.match[mlen++] = cells[k];
+                const bool horizontal = (cells[0] / C) == (cells[1] / C);
+                name = (horizontal && sp_h) ? NAME_HLASER : (sp_v ? NAME_VLASER : NAME_NORMAL);
+                have = true;
+            } else {
+                int hit = -1, shared = -1;
+                if (sp_bomb) {                               // ref :304-308: first queued line sharing a cell
+                    for (int q = qh; q < qn && hit < 0; ++q) {
+                        const int lj = s.order[q];
+                        for (int k = 0; k < len && hit < 0; ++k)
+                            for (int u = 0; u < s.line_len[lj]; ++u)
+                                if (s.line_cells[lj][u] == cells[k]) { hit = q; shared = cells[k]; break; }
+                    }
+                }
+                if (hit >= 0) {                              // ref :309-320
+                    const int lj = s.order[hit];
+                    const int llen = s.line_len[lj];
+                    uint16_t* lc = s.line_cells[lj];
+                    const int sr = shared / C, scc = shared % C;
+                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
+                    // first three of the stable sort of l by Manhattan distance (ref :310)
+                    int picked[3] = {-1, -1, -1};
+                    const int take = llen < 3 ? llen : 3;
+                    for (int a = 0; a < take; ++a) {
+                        int bi = -1, bd = 0;
+                        for (int u = 0; u < llen; ++u) {
+                            if (u == picked[0] || u == picked[1]) continue;
+                            const int d = abs(lc[u] / C - sr) + abs(lc[u] % C - scc);
+                            if (bi < 0 || d < bd) { bi = u; bd = d; }
+                        }
+                        picked[a] = bi;
+                        bool in_line = false;
+                        for (int k = 0; k < len; ++k) in_line |= (cells[k] == lc[bi]);
+                        if (!in_line) s.match[mlen++] = lc[bi];  // ref :312
+                    }
+                    name = NAME_BOMB; have = true;
+                    if (llen < 6) {                          // ref :315-316 (lines are distinct by value)
+                        for (int q = hit; q + 1 < qn; ++q) s.order[q] = s.order[q + 1];
+                        --qn;
+                    } else {                                 // ref :317-319: drop the three cells, keep the order
+                        int w = 0;
+                        for (int u = 0; u < llen; ++u)
+                            if (u != picked[0] && u != picked[1] && u != picked[2]) lc[w++] = lc[u];
+                        s.line_len[lj] = (uint8_t)w;
+                    }
+                } else if (len >= 3) {                       // ref :322-325
+                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
+                    have = true;
+                }
+            }
+            if (!have) continue;
+            if (name != NAME_NORMAL) {                       // ref :414-418
+                const int pos = creation_pos(mlen, ntaken, name != NAME_BOMB);
+                if (pos >= 0 && ntaken < CF::ML) s.taken[ntaken++] = (uint16_t)pos;
+                if (ncq < CF::ML) {
+                    s.cq_pos[ncq] = (uint16_t)(pos < 0 ? 0xffff : pos);
+                    s.cq_type[ncq] = (int8_t)name;
+                    s.cq_colour[ncq] = (uint8_t)colour;
+                    ++ncq;
+                }
+            }
+            for (int k = 0; k < mlen; ++k) {                 // ref :460-471
+                const int cell = s.match[k];
+                const int t = typ[cell];
+                if (not01(t)) activate(cell, t, true);
+                else del_cell(cell);
+            }
+        }
+        for (int i = 0; i < ncq; ++i) {                      // ref :426-427 -> create_special :572-597
+            ++n_new;
+            if (s.cq_pos[i] == 0xffff) continue;
+            col[s.cq_pos[i]] = (int8_t)s.cq_colour[i];
+            typ[s.cq_pos[i]] = s.cq_type[i];
+        }
+    }
+
+    // one cascade round without gravity/refill (ref :369-373); returns the number of lines found
+    __device__ int resolve_round(int from) {
+        sync();
+        const Scan sc = scan_lines(from);
+        if (sc.rstar < 0) return 0;
+        const int n = build_line_table(sc);
+        if (lane == 0) { nzc = -1; process_and_resolve(n); }
+        sync();
+        return n;
+    }
+
+    // combination_match (ref :600-719), leader lane
+    __device__ void combination(int i1, int i2) {
+        n_act += 2;                                          // ref :609
+        nzc = -1;
+        int t1 = typ[i1], k1 = col[i1], t2 = typ[i2], k2 = col[i2];
+        const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
+        if (t1 == -1 && t2 == -1) {                          // ref :615-616
+            for (int i = 0; i < P; ++i) { col[i] = 0; typ[i] = 0; }
+        } else if ((t1 == -1 && t2 == 1) || (t1 == 1 && t2 == -1)) {  // ref :619-641
+            const int ck = (t1 == -1) ? i1 : i2;
+            const int kk = (t1 == -1) ? k2 : k1;
+            del_cell(ck);                                    // ref :626,628
+            for (int i = 0; i < P; ++i) if (col[i] == kk && typ[i] == 1) del_cell(i);   // ref :631-635
+            // snapshot mask colour==kk & type>1, visited row-major; cells can only disappear meanwhile (ref :638-640)
+            for (int i = 0; i < P; ++i)
+                if (col[i] == kk && typ[i] > 1) activate(i, typ[i], false);
+            n_act -= 1;                                      // ref :641
+        } else if ((t1 == -1 && t2 >= 2) || (t1 >= 2 && t2 == -1)) {  // ref :644-660
+            const int ck = (t1 == -1) ? i1 : i2;
+            const int kk = (t1 == -1) ? k2 : k1;
+            const int tt = (t1 == -1) ? t2 : t1;
+            del_cell(ck);                                    // ref :651
+            // ref :654 snapshot of colour==kk; a cell leaves the snapshot only by deletion (colour -> 0), and a cell
+            // that was not in it never gains the colour, so a live test of colour==kk is the same set.  kk == 0 would
+            // also select emptied cells, but their type is 0 and they are skipped either way.
+            for (int i = 0; i < P; ++i) if (col[i] == kk && typ[i] == 1) typ[i] = (int8_t)tt;  // ref :655-657
+            for (int i = 0; i < P; ++i)
+                if (col[i] == kk && not01(typ[i])) activate(i, typ[i], false);                 // ref :660
+        } else if ((t1 == 2 || t1 == 3) && (t2 == 2 || t2 == 3)) {    // ref :663-674
+            del_cell(i1); del_cell(i2);
+            const int cell = min(r1, r2) * C + min(c1, c2);
+            activate(cell, 2, false);
+            activate(cell, 3, false);
+        } else if ((t1 == 4 && (t2 == 2 || t2 == 3)) || (t2 == 4 && (t1 == 2 || t1 == 3))) {  // ref :677-696
+            del_cell(i1); del_cell(i2);
+            const int r = min(r1, r2), c = min(c1, c2);
+            const int min_r = max(r - 1, 0), max_r = min(r + 1, R - 1);
+            const int min_c = max(c - 1, 0), max_c = min(c + 1, C - 1);
+            for (int i = min_r; i <= max_r; ++i) activate(i * C + c, 3, false);
+            for (int j = min_c; j <= max_c; ++j) activate(r * C + j, 2, false);
+        } else if (t1 == 4 && t2 == 4) {                     // ref :699-719
+            del_cell(i1); del_cell(i2);
+            const int r = min(r1, r2), c = min(c1, c2);
+            const int min_r = max(r - 2, 0), max_r = min(r + 2, R - 1);
+            const int min_c = max(c - 2, 0), max_c = min(c + 2, C - 1);
+            for (int i = min_r; i <= max_r; ++i)
+                for (int j = min_c; j <= max_c; ++j) {
+                    const int q = i * C + j;
+                    if (typ[q] == 1) del_cell(q);
+                    else if (typ[q] != 0) activate(q, typ[q], false);
+                }
+        }
+    }
+
+    // shuffle (ref :114-118): new[i] = old[perm[i]], perm = Fisher-Yates of arange(P) on stream 1.  Applying the
+    // same swaps to the cells themselves yields exactly old[perm[i]].  Leader lane.
+    __device__ void shuffle_serial() {
+        uint32_t w[4];
+        uint64_t have_blk = ~0ull;
+        for (int i = P - 1; i >= 1; --i) {
+            const uint64_t k = scur++;
+            const uint64_t blk = k >> 2;
+            if (blk != have_blk) {
+                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), gid, 1u, p.key0, p.key1, w);
+                have_blk = blk;
+            }
+            const uint32_t word = (k & 3) == 0 ? w[0] : (k & 3) == 1 ? w[1] : (k & 3) == 2 ? w[2] : w[3];
+            const int j = (int)__umulhi(word, (uint32_t)(i + 1));
+            const int8_t a = col[i], b = typ[i];
+            col[i] = col[j]; typ[i] = typ[j];
+            col[j] = a; typ[j] = b;
+        }
+    }
+    __device__ void shuffle() {
+        sync();
+        const uint64_t s0 = scur;
+        if (lane == 0) shuffle_serial();
+        scur = s0 + (uint64_t)(P > 1 ? P - 1 : 0);  // one word per Fisher-Yates step, on every lane
+        sync();
+    }
+
+    // ===================================================================================================
+    // is_move_effective (ref :735-787)
+    // ===================================================================================================
+    __device__ __forceinline__ void action_cells(int a, int& i1, int& i2) const {  // ref :80-91
+        const int nv = C * (R - 1);
+        if (a < nv) { i1 = a; i2 = a + C; }
+        else {
+            const int j = a - nv;
+            const int r = j / (C - 1), c = j - r * (C - 1);
+            i1 = r * C + c; i2 = i1 + 1;
+        }
+    }
+    // literal window rule, evaluated by ONE lane with a virtual swap (the board is not touched)
+    __device__ bool effective_literal(int i1, int i2) const {
+        const int ta = typ[i1], tb = typ[i2];
+        if (not01(ta) && not01(tb)) return true;             // ref :750
+        if (ta < 0 || tb < 0) return true;                   // ref :754
+        const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
+        const int rmin_ = max(0, min(r1, r2) - 2), rmax_ = min(R - 1, max(r1, r2) + 2);  // ref :758-761
+        const int cmin_ = max(0, min(c1, c2) - 2), cmax_ = min(C - 1, max(c1, c2) + 2);
+        auto cs = [&](int i) -> int { return i == i1 ? col[i2] : (i == i2 ? col[i1] : col[i]); };
+        auto ts = [&](int i) -> int { return i == i1 ? typ[i2] : (i == i2 ? typ[i1] : typ[i]); };
+        if (cmin_ + 2 <= cmax_)                               // ref :767-771
+            for (int r = rmin_; r <= rmax_; ++r)
+                for (int c = cmin_; c + 2 <= cmax_; ++c) {
+                    const int i = r * C + c;
+                    if (cs(i) == cs(i + 1) && cs(i + 1) == cs(i + 2) && ts(i + 2) >= 0) return true;
+                }
+        if (rmin_ + 2 <= rmax_)                               // ref :777-781
+            for (int r = rmin_; r + 2 <= rmax_; ++r)
+                for (int c = cmin_; c <= cmax_; ++c) {
+                    const int i = r * C + c;
+                    if (cs(i) == cs(i + C) && cs(i + C) == cs(i + 2 * C) && ts(i + 2 * C) >= 0) return true;
+                }
+        return false;
+    }
+    // one action, all lanes cooperate: lane j tests window row j (horizontal triples) and window column j (vertical)
+    __device__ bool effective_group(int a) {
+        int i1, i2;
+        action_cells(a, i1, i2);
+        const int ta = typ[i1], tb = typ[i2];
+        if (not01(ta) && not01(tb)) return true;
+        if (ta < 0 || tb < 0) return true;
+        const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
+        const int rmin_ = max(0, min(r1, r2) - 2), rmax_ = min(R - 1, max(r1, r2) + 2);
+        const int cmin_ = max(0, min(c1, c2) - 2), cmax_ = min(C - 1, max(c1, c2) + 2);
+        auto cs = [&](int i) -> int { return i == i1 ? col[i2] : (i == i2 ? col[i1] : col[i]); };
+        auto ts = [&](int i) -> int { return i == i1 ? typ[i2] : (i == i2 ? typ[i1] : typ[i]); };
+        bool f = false;
+        const int r = rmin_ + lane;
+        if (r <= rmax_)
+            for (int c = cmin_; c + 2 <= cmax_; ++c) {
+                const int i = r * C + c;
+                f |= (cs(i) == cs(i + 1) && cs(i + 1) == cs(i + 2) && ts(i + 2) >= 0);
+            }
+        const int c = cmin_ + lane;
+        if (c <= cmax_)
+            for (int rr = rmin_; rr + 2 <= rmax_; ++rr) {
+                const int i = rr * C + c;
+                f |= (cs(i) == cs(i + C) && cs(i + C) == cs(i + 2 * C) && ts(i + 2 * C) >= 0);
+            }
+        return ballot(f) != 0u;
+    }
+
+    // ===================================================================================================
+    // legal-move mask (ref tile_match_env.py:118-124) by row bitboards: lane c holds, per colour k, the set of
+    // rows of column c that carry k.  effv bit r <-> action r*C+c (swap with the cell below);
+    // effh bit r <-> action C(R-1) + r(C-1) + c (swap with the cell to the right).
+    // Boards with a pre-existing triple inside some window, or with a coloured tile of negative type, take the
+    // literal per-action path (their masks depend on the exact window rule).
+    // ===================================================================================================
+    __device__ void mask_bits(unsigned& effv, unsigned& effh, bool& any) {
+        sync();
+        const bool in = lane < C;
+        unsigned S = 0u, Ng = 0u;    // rows with type not in {0,1} / type < 0
+        bool odd = false;            // coloured tile with negative type, or colour 0 with type >= 0
+        if (in)
+            for (int r = 0; r < R; ++r) {
+                const int t = typ[r * C + lane], x = col[r * C + lane];
+                S |= (unsigned)not01(t) << r;
+                Ng |= (unsigned)(t < 0) << r;
+                odd |= (t < 0) != (x == 0);
+            }
+        const unsigned rows_v = (R >= 32 ? 0xffffffffu : ((1u << R) - 1u)) >> 1;  // rows r with r+1 < R
+        effv = ((S & (S >> 1)) | Ng | (Ng >> 1)) & rows_v;                        // ref :750,754
+        effh = (S & from_right(S, 1)) | Ng | from_right(Ng, 1);
+        unsigned unstable = 0u;
+        for (int k = 1; k <= K; ++k) {
+            unsigned b = 0u;
+            if (in)
+                for (int r = 0; r < R; ++r) b |= (unsigned)(col[r * C + lane] == k) << r;
+            const unsigned l1 = from_left(b, 1), l2 = from_left(b, 2), r1 = from_right(b, 1), r2 = from_right(b, 2);
+            const unsigned hl = l1 & l2, hm = l1 & r1, hr = r1 & r2;      // a k-tile placed here completes a row triple
+            const unsigned vu = (b << 1) & (b << 2), vm = (b << 1) & (b >> 1), vd = (b >> 1) & (b >> 2);
+            const unsigned hany = hl | hm | hr, vany = vu | vm | vd;
+            unstable |= (b & (b >> 1) & (b >> 2)) | (b & r1 & r2);
+            // horizontal swap (r,c)<->(r,c+1): the k-tile on the right moves here, or the k-tile here moves right
+            effh |= (r1 & (hl | vany)) | (b & from_right(hr | vany, 1));
+            // vertical swap (r,c)<->(r+1,c): the k-tile below moves up, or the k-tile here moves down
+            effv |= ((b >> 1) & (vu | hany)) | (b & ((vd | hany) >> 1));
+        }
+        if (!in || lane + 1 >= C) effh = 0u;
+        if (!in) effv = 0u;
+        effv &= rows_v;
+        effh &= (R >= 32 ? 0xffffffffu : ((1u << R) - 1u));
+        if (ballot(unstable != 0u || odd)) {  // literal window rule, one action at a time per lane (rare)
+            effv = 0u; effh = 0u;
+            if (in)
+                for (int r = 0; r < R; ++r) {
+                    const int i = r * C + lane;
+                    if (r + 1 < R) effv |= (unsigned)effective_literal(i, i + C) << r;
+                    if (lane + 1 < C) effh |= (unsigned)effective_literal(i, i + 1) << r;
+                }
+        }
+        any = ballot((effv | effh) != 0u) != 0u;
+    }
+    __device__ void mask_to_smem(unsigned effv, unsigned effh) {
+        if (lane < C) {
+            const int nv = C * (R - 1);
+            for (int r = 0; r < R; ++r) {
+                if (r + 1 < R) s.mask[r * C + lane] = (uint8_t)((effv >> r) & 1u);
+                if (lane + 1 < C) s.mask[nv + r * (C - 1) + lane] = (uint8_t)((effh >> r) & 1u);
+            }
+        }
+    }
+
+    // ===================================================================================================
+    // playability loop shared by generate_board (ref :99-109) and move (ref :381-391)
+    // ===================================================================================================
+    // `clean`: the caller knows the board has no lines.  Leaves the mask bits of the final board in effv/effh.
+    __device__ bool playability(bool clean, unsigned& effv, unsigned& effh) {
+        bool shuffled = false;
+        int iters = 0, from = R - 1;
+        for (;;) {
+            if (!clean) {
+                sync();
+                const Scan sc = scan_lines(from);
+                if (sc.rstar >= 0) {                         // remove_colour_lines (ref :120-131)
+                    if (iters >= p.max_iters) { status |= ST_RESET_CAP; break; }
+                    ++iters;
+                    const int top = first_line_top(sc);
+                    const int row = min(R - 1, top + 1);
+                    draw_cells((row + 1) * C, false);
+                    // rows below max(rstar, row+2) were line-free before and none of their 3-windows changed
+                    from = min(R - 1, max(sc.rstar, row + 2));
+                    continue;
+                }
+            }
+            bool any;
+            mask_bits(effv, effh, any);
+            if (any) return shuffled;                        // possible_move (ref :558-569)
+            if (iters >= p.max_iters) { status |= ST_RESET_CAP; return shuffled; }
+            ++iters;
+            shuffled = true;
+            shuffle();
+            clean = false;
+            from = R - 1;
+        }
+        bool any;
+        mask_bits(effv, effh, any);
+        return shuffled;
+    }
+
+    // generate_board (ref :95-112)
+    __device__ void generate(unsigned& effv, unsigned& effh) {
+        draw_cells(P, true);
+        playability(false, effv, effh);
+    }
+
+    // move (ref :330-395) after the effectiveness gate; i1/i2 are the swapped cells
+    __device__ void move(int i1, int i2, int& reward, int& is_comb, int& shuffled, unsigned& effv, unsigned& effh) {
+        n_new = 0; n_act = 0;                                // ref :343-347
+        int elim = 0;
+        sync();
+        if (lane == 0) {                                     // swap_coords (ref :355, :729-732)
+            const int8_t a = col[i1], b = typ[i1];
+            col[i1] = col[i2]; typ[i1] = typ[i2];
+            col[i2] = a; typ[i2] = b;
+        }
+        sync();
+        const int t1 = typ[i1], t2 = typ[i2];
+        const bool comb = (not01(t1) && not01(t2)) || t1 < 0 || t2 < 0;  // ref :357-359
+        is_comb = comb;
+        sync();  // every lane has read the swapped types before the leader starts deleting
+        if (comb) {
+            if (lane == 0) combination(i1, i2);              // ref :361
+            int e_cnt;
+            const int e = gravity(&e_cnt);                   // ref :362-363
+            elim += e_cnt;
+            refill(e);                                       // ref :364
+        }
+        for (;;) {                                           // ref :367-376
+            if (resolve_round(R - 1) == 0) break;
+            int e_cnt;
+            const int e = gravity(&e_cnt);
+            elim += e_cnt;
+            refill(e);
+        }
+        shuffled = playability(true, effv, effh);            // ref :381-391
+        n_new = shfl(n_new, 0);
+        n_act = shfl(n_act, 0);
+        reward = elim + n_new;                               // ref :378
+    }
+
+    __device__ bool board_is_valid() {
+        bool bad = false;
+        for (int i = lane; i < P; i += L) {
+            const int k = col[i], t = typ[i];
+            bad |= !((t == -1 && k == 0) || (t >= 1 && t <= 4 && k >= 1 && k <= K));
+        }
+        return ballot(bad) == 0u;
+    }
+};
+
+// ======================================================================================================
+// kernels
+// ======================================================================================================
+template <int L> struct GroupCtx {
+    int g, lane, env, gshift;
+    unsigned gmask;
+    __device__ GroupCtx() {
+        g = (int)threadIdx.x / L;
+        lane = (int)threadIdx.x % L;
+        env = (int)blockIdx.x * Cfg<L>::GPB + g;
+        gshift = ((int)threadIdx.x & 31) & ~(L - 1);
+        gmask = Cfg<L>::LMASK << gshift;
+    }
+};
+
+template <int L> __device__ __forceinline__ GroupSmem<L>& group_smem(int g) {
+    extern __shared__ __align__(16) unsigned char tmg_smem_raw[];
+    return reinterpret_cast<GroupSmem<L>*>(tmg_smem_raw)[g];
+}
+
+template <int L> __device__ __forceinline__ void write_step_outputs(const Params& p, int env, int lane, int timer,
+                                                                    int reward, int terminated, int is_comb, int n_new,
+                                                                    int n_act, int shuffled, bool write_timer = true) {
+    if (lane == 0) {
+        if (write_timer) {
+            p.timer[env] = timer;
+            p.moves_left[env] = p.num_moves - timer;
+        }
+        p.reward[env] = reward;
+        p.terminated[env] = (uint8_t)terminated;
+        p.is_comb[env] = (uint8_t)is_comb;
+        p.new_specials[env] = n_new;
+        p.activated[env] = n_act;
+        p.shuffled[env] = (uint8_t)shuffled;
+    }
+}
+template <int L> __device__ __forceinline__ void merge_status(Board<L>& b, const Params& p) {
+    const unsigned st = b.ror(b.status);
+    if (st && b.lane == 0) p.status[b.env] |= st;
+}
+
+// TileMatchEnv.reset (ref tile_match_env.py:84-91) for the selected envs
+template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(const Params p) {
+    const GroupCtx<L> gc;
+    if (gc.env >= p.N) return;
+    if (p.reset_mask && !p.reset_mask[gc.env]) return;
+    Board<L> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
+    b.load_cursors();
+    unsigned effv = 0u, effh = 0u;
+    if (p.init_boards) {
+        b.load_board(p.init_boards, p.init_vecw);
+        if (!b.board_is_valid()) b.status |= ST_INVALID_BOARD;
+        bool any;
+        b.mask_bits(effv, effh, any);
+    } else {
+        b.generate(effv, effh);
+    }
+    b.store_board();
+    b.store_cursors();
+    if (!(p.flags & FLAG_NO_MASK)) { b.mask_to_smem(effv, effh); b.store_mask(); }
+    merge_status(b, p);
+    write_step_outputs<L>(p, gc.env, gc.lane, 0, 0, 0, 0, 0, 0, 0);
+}
+
+// TileMatchEnv.step (ref tile_match_env.py:93-112)
+template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const Params p) {
+    const GroupCtx<L> gc;
+    if (gc.env >= p.N) return;
+    const int env = gc.env, lane = gc.lane;
+    Board<L> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
+    const bool want_mask = !(p.flags & FLAG_NO_MASK);
+    int timer = p.timer[env];
+    const int action = p.actions[env];
+    unsigned effv = 0u, effh = 0u;
+    if (timer < 0 || timer >= p.num_moves) {
+        if (p.autoreset == AUTORESET_NEXT_STEP && timer >= p.num_moves) {  // this call is the reset
+            b.load_cursors();
+            b.generate(effv, effh);
+            b.store_board();
+            b.store_cursors();
+            if (want_mask) { b.mask_to_smem(effv, effh); b.store_mask(); }
+            merge_status(b, p);
+            write_step_outputs<L>(p, env, lane, 0, 0, 0, 0, 0, 0, 0);
+            return;
+        }
+        b.sync();
+        if (lane == 0) p.status[env] |= ST_NEEDS_RESET;                    // ref tile_match_env.py:94-95
+        write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
+        return;
+    }
+    if (action < 0 || action >= p.A) {                                     // ref tile_match_env.py:97
+        b.sync();
+        if (lane == 0) p.status[env] |= ST_BAD_ACTION;
+        write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
+        return;
+    }
+    // effectiveness gate (ref board.py:352): the maintained mask IS is_move_effective of the current board
+    bool eff, have_board = false;
+    if (want_mask) {
+        eff = p.mask[(size_t)env * p.A + action] != 0;
+    } else {
+        b.load_board(p.board, p.board_vecw);
+        have_board = true;
+        eff = b.effective_group(action);
+    }
+    b.sync();  // every lane has read timer/action/gate before any lane of the group writes state back
+    int reward = 0, is_comb = 0, shuffled = 0;
+    bool dirty = false;
+    if (eff) {
+        if (!have_board) b.load_board(p.board, p.board_vecw);
+        b.load_cursors();
+        int i1, i2;
+        b.action_cells(action, i1, i2);
+        b.move(i1, i2, reward, is_comb, shuffled, effv, effh);
+        dirty = true;
+    }
+    ++timer;                                                               // ref tile_match_env.py:100-101
+    const int terminated = timer == p.num_moves;
+    const int n_new = b.n_new, n_act = b.n_act;
+    bool zero_mask = false;
+    if (terminated) {
+        if (p.autoreset == AUTORESET_SAME_STEP) {
+            if (!dirty) b.load_cursors();
+            b.generate(effv, effh);
+            dirty = true;
+            timer = 0;
+        } else {
+            zero_mask = true;                                              // ref tile_match_env.py:119-120
+        }
+    }
+    if (dirty) { b.store_board(); b.store_cursors(); }
+    if (want_mask) {
+        if (zero_mask) b.store_zero_mask();
+        else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); }
+    }
+    merge_status(b, p);
+    write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled);
+}
+
+// _get_effective_actions for every env from its current board (ref tile_match_env.py:118-124)
+template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_mask(const Params p) {
+    const GroupCtx<L> gc;
+    if (gc.env >= p.N) return;
+    Board<L> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
+    const bool terminal = p.timer[gc.env] == p.num_moves;
+    b.sync();
+    if (terminal) { b.store_zero_mask(); return; }
+    b.load_board(p.board, p.board_vecw);
+    unsigned effv, effh;
+    bool any;
+    b.mask_bits(effv, effh, any);
+    b.mask_to_smem(effv, effh);
+    b.store_mask();
+}
+
+// one engine primitive per env (known-answer replays of the reference's function-level tests)
+template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(const Params p) {
+    const GroupCtx<L> gc;
+    if (gc.env >= p.N) return;
+    const int env = gc.env, lane = gc.lane;
+    Board<L> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
+    b.load_board(p.board, p.board_vecw);
+    b.load_cursors();
+    b.n_new = p.new_specials[env];
+    b.n_act = p.activated[env];
+    const int a0 = p.dbg_args ? p.dbg_args[env * 4 + 0] : 0, a1 = p.dbg_args ? p.dbg_args[env * 4 + 1] : 0;
+    const int a2 = p.dbg_args ? p.dbg_args[env * 4 + 2] : 0, a3 = p.dbg_args ? p.dbg_args[env * 4 + 3] : 0;
+    int result = 0;
+    const int C = p.C;
+    switch (p.dbg_op) {
+        case OP_GRAVITY: b.gravity(&result); break;
+        case OP_REFILL: {
+            int e = 0;  // refill() expects the post-gravity layout; a general board is handled row by row instead
+            b.sync();
+            // count empties row-major and assign draws in that order (ref :231-241)
+            int total = 0;
+            for (int r = 0; r < p.R; ++r) {
+                const bool em = lane < C && b.col[r * C + lane] == 0 && b.typ[r * C + lane] == 0;
+                const unsigned m = b.ballot(em);
+                total += __popc(m);
+            }
+            for (int ps = 0; ps < total; ps += Cfg<L>::NW) {
+                const int nw = min(Cfg<L>::NW, total - ps);
+                if (!p.use_inj) b.fill_words(0u, b.dcur + (uint64_t)ps, nw);
+                int base = 0;
+                for (int r = 0; r < p.R; ++r) {
+                    const bool em = lane < C && b.col[r * C + lane] == 0 && b.typ[r * C + lane] == 0;
+                    const unsigned m = b.ballot(em);
+                    if (em) {
+                        const int rank = base + __popc(m & b.lt_mask());
+                        if (rank >= ps && rank < ps + nw) {
+                            b.col[r * C + lane] = (int8_t)b.draw_colour(rank, rank - ps);
+                            b.typ[r * C + lane] = 1;
+                        }
+                    }
+                    base += __popc(m);
+                }
+                b.sync();
+            }
+            b.dcur += (uint64_t)total;
+            (void)e;
+            result = total;
+            break;
+        }
+        case OP_RESOLVE_ROUND: result = b.resolve_round(p.R - 1); break;
+        case OP_ACTIVATE:
+            if (lane == 0) { b.nzc = -1; b.activate(a0 * C + a1, a2, a3 == 0); }
+            break;
+        case OP_COMBINE:
+            if (lane == 0) b.combination(a0 * C + a1, a2 * C + a3);
+            break;
+        case OP_MOVE: {
+            int reward = 0, is_comb = 0, shuffled = 0;
+            unsigned effv = 0u, effh = 0u;
+            const int i1 = a0 * C + a1, i2 = a2 * C + a3;
+            b.n_new = 0; b.n_act = 0;
+            bool eff = false;
+            if (lane == 0) eff = b.effective_literal(i1, i2);
+            eff = b.shfl((int)eff, 0) != 0;
+            if (eff) b.move(i1, i2, reward, is_comb, shuffled, effv, effh);
+            if (lane == 0) { p.is_comb[env] = (uint8_t)is_comb; p.shuffled[env] = (uint8_t)shuffled; }
+            result = reward;
+            break;
+        }
+        case OP_EFFECTIVE: {
+            bool eff = false;
+            if (lane == 0) eff = b.effective_literal(a0 * C + a1, a2 * C + a3);
+            result = b.shfl((int)eff, 0);
+            break;
+        }
+        case OP_GENERATE: { unsigned v, h; b.generate(v, h); break; }
+        case OP_SHUFFLE: b.shuffle(); break;
+        case OP_COUNT_LINES: {
+            b.sync();
+            const typename Board<L>::Scan sc = b.scan_lines(p.R - 1);
+            result = sc.rstar < 0 ? 0 : b.build_line_table(sc);
+            break;
+        }
+        default: break;
+    }
+    b.n_new = b.shfl(b.n_new, 0);
+    b.n_act = b.shfl(b.n_act, 0);
+    b.store_board();
+    b.store_cursors();
+    if (lane == 0) {
+        p.reward[env] = result;
+        p.new_specials[env] = b.n_new;
+        p.activated[env] = b.n_act;
+    }
+    merge_status(b, p);
+}
+
+// OneHotWrapper._one_hot_encode_board (ref wrappers.py:54-69).  One thread per 4 output bytes (or 1 float4).
+template <typename OUT> __global__ void __launch_bounds__(256) k_onehot(const Params p, OUT* __restrict__ out, int planes) {
+    const long long total = (long long)p.N * planes * p.P;
+    const long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q0 >= total) return;
+    const int pp = planes * p.P;
+    OUT v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long q = q0 + j;
+        OUT o = (OUT)0;
+        if (q < total) {
+            const int env = (int)(q / pp);
+            const int rem = (int)(q - (long long)env * pp);
+            const int plane = rem / p.P, cell = rem - plane * p.P;
+            const int8_t* bd = p.board + (size_t)env * 2 * p.P;
+            if (plane < p.K) o = (OUT)(bd[cell] == plane + 1);
+            else {  // enabled specials in the order cookie(-1), v(2), h(3), bomb(4) (ref wrappers.py:40-46)
+                int idx = plane - p.K, want = 99;
+                if (p.specials & SP_COOKIE) { if (idx == 0) want = -1; --idx; }
+                if (p.specials & SP_VLASER) { if (idx == 0) want = 2; --idx; }
+                if (p.specials & SP_HLASER) { if (idx == 0) want = 3; --idx; }
+                if (p.specials & SP_BOMB) { if (idx == 0) want = 4; --idx; }
+                o = (OUT)(bd[p.P + cell] == want);
+            }
+        }
+        v[j] = o;
+    }
+    if (q0 + 3 < total) {
+        if (sizeof(OUT) == 1) {
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(out) + q0) =
+                (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[q0 + j] = v[j];
+        }
+    } else {
+        for (int j = 0; j < 4 && q0 + j < total; ++j) out[q0 + j] = v[j];
+    }
+}
+
+__global__ void k_clear_status(uint32_t* st, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) st[i] = 0u;
+}
+
+}  // namespace tmg
