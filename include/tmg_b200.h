@@ -153,6 +153,9 @@ int tmg_encode_onehot_f32(tmg_env *env, float *out_dev, void *stream);
 
 int tmg_clear_status(tmg_env *env, void *stream);
 
+/* TileMatchEnv.reset(seed=...) / set_seed (tile_match_env.py:79-86): new Philox key, both cursors back to 0 */
+int tmg_set_seed(tmg_env *env, uint64_t seed, void *stream);
+
 /* Host-buffer convenience path (the call a CPU-side consumer makes): copies actions from host memory,
  * steps, and copies back whatever output pointers are non-NULL; synchronises the stream before
  * returning.  Pinned host memory makes the copies asynchronous DMA. */

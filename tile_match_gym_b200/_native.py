@@ -1,0 +1,125 @@
+"""ctypes binding of libtmg_b200.so (include/tmg_b200.h).  There is no CPU fallback: if the CUDA
+library is missing or no B200 is present, constructing an env raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libtmg_b200.so")
+SRC = os.path.join(_HERE, "csrc", "tmg_b200.cu")
+DEVICE_HDR = os.path.join(_HERE, "csrc", "tmg_device.cuh")
+ABI_HDR = os.path.join(ROOT, "include", "tmg_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+SP_COOKIE, SP_VERTICAL_LASER, SP_HORIZONTAL_LASER, SP_BOMB = 1, 2, 4, 8
+SPECIAL_BITS = {"cookie": SP_COOKIE, "vertical_laser": SP_VERTICAL_LASER,
+                "horizontal_laser": SP_HORIZONTAL_LASER, "bomb": SP_BOMB}
+AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
+REFILL = {"philox": 0, "injected": 1}
+FLAG_NO_MASK = 1
+
+ST_BAD_ACTION, ST_NEEDS_RESET, ST_DRAWS_EXHAUSTED, ST_RESET_CAP = 1, 2, 4, 8
+ST_LINE_OVERFLOW, ST_DFS_OVERFLOW, ST_INVALID_BOARD, ST_INTERNAL = 16, 32, 64, 128
+
+OPS = {"gravity": 1, "refill": 2, "resolve_round": 3, "activate": 4, "combine": 5, "move": 6, "effective": 7,
+       "generate": 8, "shuffle": 9, "count_lines": 10}
+
+
+class Config(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("num_envs", C.c_int32),
+                ("num_rows", C.c_int32), ("num_cols", C.c_int32), ("num_colours", C.c_int32),
+                ("num_moves", C.c_int32), ("specials", C.c_uint32), ("autoreset", C.c_int32),
+                ("refill_mode", C.c_int32), ("flags", C.c_uint32), ("max_reset_iters", C.c_int32),
+                ("seed", C.c_uint64), ("env_id_offset", C.c_uint64)]
+
+
+BUFFER_FIELDS = ["board", "timer", "draw_cursor", "shuffle_cursor", "reward", "terminated",
+                 "is_combination_match", "num_new_specials", "num_specials_activated", "shuffled", "mask",
+                 "num_moves_left", "status"]
+
+
+class Buffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in BUFFER_FIELDS]
+
+
+HOST_IO_FIELDS = ["actions", "board", "reward", "terminated", "mask", "num_moves_left", "is_combination_match",
+                  "num_new_specials", "num_specials_activated", "shuffled", "status"]
+
+
+class HostIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in HOST_IO_FIELDS]
+
+
+EXPORTS = {
+    "tmg_abi_version": (C.c_int, []),
+    "tmg_error_string": (C.c_char_p, [C.c_int]),
+    "tmg_status_string": (C.c_char_p, [C.c_uint32]),
+    "tmg_num_actions": (C.c_int, [C.c_int32, C.c_int32]),
+    "tmg_onehot_planes": (C.c_int, [C.c_int32, C.c_uint32]),
+    "tmg_action_to_coords": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32 * 4)]),
+    "tmg_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "tmg_destroy": (C.c_int, [C.c_void_p]),
+    "tmg_get_buffers": (C.c_int, [C.c_void_p, C.POINTER(Buffers)]),
+    "tmg_set_injected_draws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "tmg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_legal_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tmg_encode_onehot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_encode_onehot_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_clear_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tmg_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tmg_step_host": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_void_p]),
+    "tmg_debug_op": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+}
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    deps = [SRC, DEVICE_HDR, ABI_HDR]
+    stale = not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
+    if force or stale:
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, SRC]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads libtmg_b200.so.  Raises if it has not been built -- the product has no other compute path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(tile_match_gym_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        if L.tmg_abi_version() != 1:
+            raise RuntimeError("libtmg_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise RuntimeError(f"tmg_b200 {what}: {lib().tmg_error_string(rc).decode()} (code {rc})")
+
+
+def specials_mask(colourless_specials, colour_specials) -> int:
+    m = 0
+    for s in list(colourless_specials) + list(colour_specials):
+        if s not in SPECIAL_BITS:
+            raise ValueError(f"unknown special {s!r}")
+        m |= SPECIAL_BITS[s]
+    return m

@@ -260,6 +260,18 @@ int tmg_clear_status(tmg_env* e, void* stream) {
     return last_error();
 }
 
+int tmg_set_seed(tmg_env* e, uint64_t seed, void* stream) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->cfg.seed = seed;
+    e->p.key0 = (uint32_t)seed;
+    e->p.key1 = (uint32_t)(seed >> 32);
+    if (cudaMemsetAsync(e->p.draw_cursor, 0, (size_t)e->p.N * 8, st) != cudaSuccess) return TMG_ERR_CUDA;
+    if (cudaMemsetAsync(e->p.shuffle_cursor, 0, (size_t)e->p.N * 8, st) != cudaSuccess) return TMG_ERR_CUDA;
+    return TMG_OK;
+}
+
 int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     if (!e || !io || !io->actions) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;

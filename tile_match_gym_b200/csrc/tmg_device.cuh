@@ -473,10 +473,10 @@ template <int L> struct Board {
         else if (t == -1) {
             kind = 3;
             if (nzc == 0) return;                  // ref :532-534
-            for (int k = 0; k <= K && k < 32; ++k) s.cnt[k] = 0;
+            for (int k = 0; k < 32; ++k) s.cnt[k] = 0;
             for (int i = 0; i < P; ++i) { const int x = col[i]; if (x > 0 && x < 32) ++s.cnt[x]; }
             int best = 0;
-            for (int k = 1; k <= K && k < 32; ++k) if (s.cnt[k] > best) { best = s.cnt[k]; mc = k; }  // ref :536-537
+            for (int k = 1; k < 32; ++k) if (s.cnt[k] > best) { best = s.cnt[k]; mc = k; }  // ref :536-537
             for (int i = 0; i < P; ++i) if (col[i] == mc && typ[i] == 1) del_cell(i);                 // ref :540-544
         } else { status |= ST_INTERNAL; return; }  // ref :555-556 raises
         if (sp >= CF::DFS) { status |= ST_DFS_OVERFLOW; return; }

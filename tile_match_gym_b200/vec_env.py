@@ -1,0 +1,374 @@
+"""TileMatchVecEnv -- drop-in *vectorised* TileMatchEnv (reference tile_match_env.py:14-150) whose
+reset/step run as hand-written sm_100a kernels behind the C ABI of include/tmg_b200.h.
+
+Same constructor arguments, spaces, reward, termination and info keys as the reference env; every
+per-env scalar becomes a length-N tensor and `info["effective_actions"]` becomes an (N, A) bool mask.
+PyTorch is only the plumbing here (device tensors that alias the engine's buffers, streams); all
+transition arithmetic happens in libtmg_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import spaces as sp
+
+ENV_ID = "TileMatch-v0"  # reference __init__.py:3
+
+
+class _DevArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it (no copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+_TYPESTR = {"board": "|i1", "timer": "<i4", "draw_cursor": "<i8", "shuffle_cursor": "<i8", "reward": "<i4",
+            "terminated": "|u1", "is_combination_match": "|u1", "num_new_specials": "<i4",
+            "num_specials_activated": "<i4", "shuffled": "|u1", "mask": "|u1", "num_moves_left": "<i4",
+            "status": "<i4"}
+
+
+class TileMatchVecEnv:
+    """N independent TileMatchEnv instances on one B200.
+
+    Args mirror `TileMatchEnv(num_rows, num_cols, num_colours, num_moves, colourless_specials,
+    colour_specials, seed=1)` (tile_match_env.py:17-27) plus:
+      num_envs        envs held by this shard
+      device          "cuda:i"
+      autoreset       "next_step" (gymnasium default), "same_step" or "disabled" (reference behaviour:
+                      stepping a finished env is an error, reported through `status`)
+      refill          "philox" (counter-based stream, see include/tmg_b200.h) or "injected"
+      env_id_offset   global id of local env 0; the draw stream of an env depends only on (seed, global id),
+                      so results are independent of how the batch is sharded over GPUs
+      compute_mask    maintain info["effective_actions"] (the reference always does)
+      obs             "int8" (aliases engine state, zero-copy), "int32" (reference dtype, one cast per call)
+                      or "onehot" (OneHotWrapper planes, uint8)
+    """
+
+    metadata = {"render_modes": ["string"], "render_fps": 2}
+
+    def __init__(self, num_envs: int, num_rows: int, num_cols: int, num_colours: int, num_moves: int,
+                 colourless_specials, colour_specials, seed: Optional[int] = 1, device="cuda:0",
+                 autoreset: str = "next_step", refill: str = "philox", env_id_offset: int = 0,
+                 compute_mask: bool = True, obs: str = "int8", max_reset_iters: int = 0,
+                 render_mode: str = "string"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tile_match_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self._lib = nat.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        self.num_envs = int(num_envs)
+        self.num_rows, self.num_cols, self.num_colours = int(num_rows), int(num_cols), int(num_colours)
+        self.num_moves = int(num_moves)
+        self.colourless_specials = list(colourless_specials)
+        self.colour_specials = list(colour_specials)
+        self.num_colour_specials = len(self.colour_specials)
+        self.num_colourless_specials = len(self.colourless_specials)
+        self.seed = 1 if seed is None else int(seed)
+        self.render_mode = render_mode
+        self.autoreset_mode = autoreset
+        self.refill = refill
+        self.env_id_offset = int(env_id_offset)
+        self.obs_mode = obs
+        if obs not in ("int8", "int32", "onehot"):
+            raise ValueError("obs must be 'int8', 'int32' or 'onehot'")
+        self.num_actions = 2 * self.num_rows * self.num_cols - self.num_rows - self.num_cols  # board.py:77
+        self.specials = nat.specials_mask(self.colourless_specials, self.colour_specials)
+        self.onehot_planes = self._lib.tmg_onehot_planes(self.num_colours, self.specials)
+        self.compute_mask = bool(compute_mask)
+
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        torch.cuda.init()
+        with torch.cuda.device(dev_index):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists before the library uses it
+        cfg = nat.Config(C.sizeof(nat.Config), dev_index, self.num_envs, self.num_rows, self.num_cols,
+                         self.num_colours, self.num_moves, self.specials, nat.AUTORESET[autoreset],
+                         nat.REFILL[refill], 0 if compute_mask else nat.FLAG_NO_MASK, int(max_reset_iters),
+                         self.seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset)
+        h = C.c_void_p()
+        nat.check(self._lib.tmg_create(C.byref(cfg), C.byref(h)), "tmg_create")
+        self._h = h
+        bufs = nat.Buffers()
+        nat.check(self._lib.tmg_get_buffers(self._h, C.byref(bufs)), "tmg_get_buffers")
+        N, R, Cc, A = self.num_envs, self.num_rows, self.num_cols, self.num_actions
+        shapes = {"board": (N, 2, R, Cc), "mask": (N, A)}
+        self._t = {}
+        for name in nat.BUFFER_FIELDS:
+            arr = _DevArray(getattr(bufs, name), shapes.get(name, (N,)), _TYPESTR[name], self)
+            self._t[name] = torch.as_tensor(arr, device=self.device)
+        # public aliases of engine state (zero-copy)
+        self.board = self._t["board"]
+        self.timer = self._t["timer"]
+        self.draw_cursor = self._t["draw_cursor"]
+        self.shuffle_cursor = self._t["shuffle_cursor"]
+        self.reward = self._t["reward"]
+        self.terminated = self._t["terminated"].view(torch.bool)
+        self.is_combination_match = self._t["is_combination_match"].view(torch.bool)
+        self.num_new_specials = self._t["num_new_specials"]
+        self.num_specials_activated = self._t["num_specials_activated"]
+        self.shuffled = self._t["shuffled"].view(torch.bool)
+        self.mask = self._t["mask"].view(torch.bool)
+        self.num_moves_left = self._t["num_moves_left"]
+        self.status = self._t["status"]
+        self.truncated = torch.zeros(N, dtype=torch.bool, device=self.device)  # tile_match_env.py:112: always False
+        self._onehot = (torch.empty((N, self.onehot_planes, R, Cc), dtype=torch.uint8, device=self.device)
+                        if obs == "onehot" else None)
+        self._injected = None
+
+        # spaces (tile_match_env.py:52-77, wrappers.py:25-30)
+        self._moves_left_observation_space = sp.Discrete(self.num_moves + 1, seed=self.seed)
+        if obs == "onehot":
+            board_space = sp.onehot_board_space(R, Cc, self.onehot_planes)
+        else:
+            board_space = sp.board_space(R, Cc, self.num_colours, self.num_colourless_specials,
+                                         self.num_colour_specials, seed=self.seed)
+        self._board_observation_space = board_space
+        self.single_observation_space = sp.Dict({"board": board_space,
+                                                 "num_moves_left": self._moves_left_observation_space})
+        self.single_action_space = sp.Discrete(self.num_actions, seed=self.seed)
+        self.observation_space = self.single_observation_space
+        self.action_space = self.single_action_space
+        # (r1,c1),(r2,c2) table, board.py:78-93
+        self._action_to_coords = tuple(self.action_to_coords(a) for a in range(self.num_actions))
+
+    # ------------------------------------------------------------------------------------------------
+    @classmethod
+    def sharded(cls, global_num_envs: int, rank: int, world_size: int, *args, **kwargs) -> "TileMatchVecEnv":
+        """Shard [0, global_num_envs) by env index: rank g owns [g*N/G, (g+1)*N/G).  No cross-GPU traffic."""
+        lo, hi = shard_range(global_num_envs, rank, world_size)
+        kwargs = dict(kwargs)
+        kwargs["env_id_offset"] = kwargs.get("env_id_offset", 0) + lo
+        return cls(hi - lo, *args, **kwargs)
+
+    def action_to_coords(self, action: int):
+        out = (C.c_int32 * 4)()
+        nat.check(self._lib.tmg_action_to_coords(self.num_rows, self.num_cols, int(action), C.byref(out)),
+                  "tmg_action_to_coords")
+        return ((out[0], out[1]), (out[2], out[3]))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            torch.cuda.synchronize(self.device)
+            self._lib.tmg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ------------------------------------------------------------------------------------------------
+    def set_seed(self, seed: int) -> None:
+        """tile_match_env.py:79-82: replaces the board generator (new key, cursors back to zero)."""
+        self.seed = int(seed)
+        nat.check(self._lib.tmg_set_seed(self._h, self.seed & 0xFFFFFFFFFFFFFFFF, self._stream()), "tmg_set_seed")
+
+    def set_injected_draws(self, draws: torch.Tensor) -> None:
+        """draws: (N, Ldraws) uint8 on this device, values 1..K; consumed in the reference's draw order."""
+        if self.refill != "injected":
+            raise RuntimeError("env was not created with refill='injected'")
+        d = draws.to(device=self.device, dtype=torch.uint8).contiguous()
+        if d.dim() != 2 or d.shape[0] != self.num_envs:
+            raise ValueError("draws must have shape (num_envs, per_env_len)")
+        self._injected = d
+        nat.check(self._lib.tmg_set_injected_draws(self._h, C.c_void_p(d.data_ptr()), d.shape[1]),
+                  "tmg_set_injected_draws")
+
+    def _obs(self):
+        if self.obs_mode == "onehot":
+            nat.check(self._lib.tmg_encode_onehot(self._h, C.c_void_p(self._onehot.data_ptr()), self._stream()),
+                      "tmg_encode_onehot")
+            board = self._onehot
+        elif self.obs_mode == "int32":
+            board = self.board.to(torch.int32)
+        else:
+            board = self.board  # aliases live state, like the reference (tile_match_env.py:115)
+        return OrderedDict([("board", board), ("num_moves_left", self.num_moves_left)])
+
+    def reset(self, seed: Optional[int] = None, options: Optional[dict] = None):
+        """tile_match_env.py:84-91.  options: {"reset_mask": bool (N,), "init_boards": int8 (N,2,R,C)}."""
+        if seed is not None:
+            self.set_seed(seed)
+        options = options or {}
+        mask = options.get("reset_mask")
+        boards = options.get("init_boards")
+        mptr = bptr = None
+        if mask is not None:
+            mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+            if mask.shape != (self.num_envs,):
+                raise ValueError("reset_mask must have shape (num_envs,)")
+            mptr = C.c_void_p(mask.data_ptr())
+        if boards is not None:
+            boards = torch.as_tensor(boards).to(device=self.device, dtype=torch.int8).contiguous()
+            if boards.shape != (self.num_envs, 2, self.num_rows, self.num_cols):
+                raise ValueError("init_boards must have shape (num_envs, 2, num_rows, num_cols)")
+            bptr = C.c_void_p(boards.data_ptr())
+        nat.check(self._lib.tmg_reset(self._h, mptr, bptr, self._stream()), "tmg_reset")
+        self._keep = (mask, boards)  # keep the inputs alive until the stream has consumed them
+        return self._obs(), {"effective_actions": self.mask}
+
+    def step(self, actions):
+        """tile_match_env.py:93-112 for every env.  actions: (N,) integer tensor."""
+        a = torch.as_tensor(actions)
+        if a.device != self.device or a.dtype != torch.int32 or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=torch.int32).contiguous()
+        if a.shape != (self.num_envs,):
+            raise ValueError("actions must have shape (num_envs,)")
+        nat.check(self._lib.tmg_step(self._h, C.c_void_p(a.data_ptr()), self._stream()), "tmg_step")
+        self._last_actions = a
+        info = {
+            "is_combination_match": self.is_combination_match,
+            "num_new_specials": self.num_new_specials,
+            "num_specials_activated": self.num_specials_activated,
+            "shuffled": self.shuffled,
+            "effective_actions": self.mask,
+        }
+        return self._obs(), self.reward, self.terminated, self.truncated, info
+
+    def legal_mask(self) -> torch.Tensor:
+        """Recompute the mask from the current boards (tile_match_env.py:118-124)."""
+        nat.check(self._lib.tmg_legal_mask(self._h, self._stream()), "tmg_legal_mask")
+        return self.mask
+
+    def onehot(self, dtype=torch.uint8) -> torch.Tensor:
+        """OneHotWrapper._one_hot_encode_board (wrappers.py:54-69) of the current boards."""
+        N, R, Cc = self.num_envs, self.num_rows, self.num_cols
+        out = torch.empty((N, self.onehot_planes, R, Cc), dtype=dtype, device=self.device)
+        if dtype == torch.uint8:
+            nat.check(self._lib.tmg_encode_onehot(self._h, C.c_void_p(out.data_ptr()), self._stream()), "onehot")
+        elif dtype == torch.float32:
+            nat.check(self._lib.tmg_encode_onehot_f32(self._h, C.c_void_p(out.data_ptr()), self._stream()), "onehot")
+        else:
+            raise ValueError("dtype must be uint8 or float32")
+        return out
+
+    def check_status(self, clear: bool = True) -> None:
+        """Raises like the reference would (Exception / IndexError / ValueError) if any env flagged an error."""
+        st = self.status
+        if not bool((st != 0).any().item()):
+            return
+        agg = 0
+        for v in torch.unique(st).tolist():
+            agg |= int(v) & 0xFFFFFFFF
+        if clear:
+            nat.check(self._lib.tmg_clear_status(self._h, self._stream()), "tmg_clear_status")
+        msg = self._lib.tmg_status_string(agg).decode()
+        if agg & nat.ST_NEEDS_RESET:
+            raise Exception("You must call reset before calling step")  # tile_match_env.py:95
+        if agg & nat.ST_BAD_ACTION:
+            raise IndexError(f"action out of range: {msg}")
+        raise RuntimeError(f"env status: {msg}")
+
+    def debug_op(self, op: str, args=None) -> None:
+        """Runs one engine primitive on every device board (known-answer tests)."""
+        a = None
+        if args is not None:
+            a = torch.as_tensor(args).to(device=self.device, dtype=torch.int32).contiguous()
+            if a.shape != (self.num_envs, 4):
+                raise ValueError("args must have shape (num_envs, 4)")
+        nat.check(self._lib.tmg_debug_op(self._h, nat.OPS[op], None if a is None else C.c_void_p(a.data_ptr()),
+                                         self._stream()), "tmg_debug_op")
+        self._dbg_keep = a
+
+    def render(self):
+        """String rendering of env 0 (tile_match_env.py:127-143 without the ANSI colour map)."""
+        b = self.board[0].cpu().numpy()
+        lines = [" " + "-" * (self.num_cols * 2 + 1)]
+        for r in range(self.num_rows):
+            lines.append("| " + " ".join(f"{b[0, r, c]}{'*' if b[1, r, c] not in (0, 1) else ''}" for c in range(self.num_cols)) + " |")
+        lines.append(" " + "-" * (self.num_cols * 2 + 1))
+        print("\n".join(lines))
+
+
+class HostStepper:
+    """The host-buffer path (tmg_step_host): actions come from pinned host memory, observations / rewards /
+    terminations / masks are copied back to pinned host memory, stream synchronised per call.  This is what a
+    CPU-side consumer of the reference API pays, and what bench.py reports as `e2e`."""
+
+    def __init__(self, env: TileMatchVecEnv, outputs=("board", "reward", "terminated", "mask", "num_moves_left")):
+        self.env = env
+        N, R, Cc, A = env.num_envs, env.num_rows, env.num_cols, env.num_actions
+        shapes = {"actions": ((N,), torch.int32), "board": ((N, 2, R, Cc), torch.int8), "reward": ((N,), torch.int32),
+                  "terminated": ((N,), torch.uint8), "mask": ((N, A), torch.uint8), "num_moves_left": ((N,), torch.int32),
+                  "is_combination_match": ((N,), torch.uint8), "num_new_specials": ((N,), torch.int32),
+                  "num_specials_activated": ((N,), torch.int32), "shuffled": ((N,), torch.uint8),
+                  "status": ((N,), torch.int32)}
+        self.host = {}
+        self.io = nat.HostIO()
+        for name in ("actions",) + tuple(outputs):
+            shape, dt = shapes[name]
+            t = torch.empty(shape, dtype=dt).pin_memory()
+            self.host[name] = t
+            setattr(self.io, name, t.data_ptr())
+        self.h2d_bytes = self.host["actions"].numel() * 4
+        self.d2h_bytes = sum(t.numel() * t.element_size() for n, t in self.host.items() if n != "actions")
+
+    def step(self, actions=None):
+        """actions: optional array-like copied into the pinned staging buffer first (int32, (N,))."""
+        if actions is not None:
+            self.host["actions"].copy_(torch.as_tensor(actions, dtype=torch.int32))
+        nat.check(self.env._lib.tmg_step_host(self.env._h, C.byref(self.io), self.env._stream()), "tmg_step_host")
+        return self.host
+
+
+def shard_range(global_num_envs: int, rank: int, world_size: int):
+    """Env-index shard owned by `rank`: [rank*N/G, (rank+1)*N/G)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    lo = global_num_envs * rank // world_size
+    hi = global_num_envs * (rank + 1) // world_size
+    return lo, hi
+
+
+class EpisodeStatistics:
+    """Optional episode statistics accumulated with a handful of elementwise torch ops per step (off the
+    transition path), with an on-demand all-reduce over the process group -- the only collective the design has
+    (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+
+    FIELDS = ("episodes", "return_sum", "length_sum", "steps", "specials_created", "specials_activated", "shuffles",
+              "combination_matches")
+
+    def __init__(self, num_envs: int, device):
+        self.device = torch.device(device)
+        self.running_return = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
+        self.running_length = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
+        self.totals = torch.zeros(len(self.FIELDS), dtype=torch.int64, device=self.device)
+
+    def update(self, reward, terminated, info) -> None:
+        r = reward.to(torch.int64)
+        term = terminated.to(torch.bool)
+        self.running_return += r
+        self.running_length += 1
+        t = self.totals
+        t[0] += term.sum()
+        t[1] += (self.running_return * term).sum()
+        t[2] += (self.running_length * term).sum()
+        t[3] += r.numel()
+        t[4] += info["num_new_specials"].to(torch.int64).sum()
+        t[5] += info["num_specials_activated"].to(torch.int64).sum()
+        t[6] += info["shuffled"].to(torch.int64).sum()
+        t[7] += info["is_combination_match"].to(torch.int64).sum()
+        keep = (~term).to(torch.int64)
+        self.running_return *= keep
+        self.running_length *= keep
+
+    def allreduce(self, group=None) -> dict:
+        """Sum of the totals over all ranks (no-op without an initialised process group)."""
+        tot = self.totals.clone()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        return dict(zip(self.FIELDS, tot.tolist()))
