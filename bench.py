@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--no-stagger", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--num-moves", type=int, default=NUM_MOVES, help="diagnostic: episode length (huge = no resets)")
+    ap.add_argument("--skip-e2e", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -162,12 +164,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_local = args.envs_per_gpu
-    env = TileMatchVecEnv(n_local, ROWS, COLS, COLOURS, NUM_MOVES, CL, CS, seed=SEED, device=dev, autoreset="same_step",
+    num_moves = args.num_moves
+    env = TileMatchVecEnv(n_local, ROWS, COLS, COLOURS, num_moves, CL, CS, seed=SEED, device=dev, autoreset="same_step",
                           env_id_offset=rank * n_local)
     env.reset()
     if not args.no_stagger:
-        env.timer.copy_((torch.arange(n_local, device=dev) + rank * n_local) % NUM_MOVES)
-        env.num_moves_left.copy_(NUM_MOVES - env.timer)
+        env.timer.copy_((torch.arange(n_local, device=dev) + rank * n_local) % num_moves)
+        env.num_moves_left.copy_(num_moves - env.timer)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     n_act = 16
     actions = [torch.randint(0, A, (n_local,), device=dev, dtype=torch.int32, generator=gen) for _ in range(n_act)]
@@ -207,7 +210,7 @@ def main():
         hs.step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(10, min(args.steps, 60))
+    e2e_steps = 3 if args.skip_e2e else max(10, min(args.steps, 60))
     e0.record(stream)
     for i in range(e2e_steps):
         hs.io.actions = host_actions[i % n_act].data_ptr()

@@ -299,6 +299,12 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     return cudaStreamSynchronize(st) == cudaSuccess ? TMG_OK : TMG_ERR_CUDA;
 }
 
+int tmg_set_profile_buffer(tmg_env* e, uint32_t* prof_dev) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    e->p.prof = prof_dev;
+    return TMG_OK;
+}
+
 int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) {
     if (!e || op < TMG_OP_GRAVITY || op > TMG_OP_COUNT_LINES) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;

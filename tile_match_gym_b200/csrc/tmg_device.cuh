@@ -76,6 +76,7 @@ struct Params {
     const int8_t* init_boards;
     const int32_t* dbg_args;
     int dbg_op;
+    uint32_t* prof;  // optional [N][4]: cycles total, cycles in leader-serial sections, cascade rounds, redraw iterations
 };
 
 template <int L> struct Cfg {
@@ -128,13 +129,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ bool not01(int t) { return t != 0 && t != 1; }
 
 // ---- vector copies between global and the group's shared memory -------------------------------------
+// (not inlined: the width switch would otherwise be replicated at every load/store site)
 template <int L, typename V> __device__ __forceinline__ void copy_vec(void* dst, const void* src, int nbytes, int lane) {
     const int n = nbytes / (int)sizeof(V);
     V* d = reinterpret_cast<V*>(dst);
     const V* s = reinterpret_cast<const V*>(src);
     for (int i = lane; i < n; i += L) d[i] = s[i];
 }
-template <int L> __device__ __forceinline__ void copy_bytes(void* dst, const void* src, int nbytes, int vecw, int lane) {
+template <int L> __device__ __noinline__ void copy_bytes(void* dst, const void* src, int nbytes, int vecw, int lane) {
     switch (vecw) {
         case 16: copy_vec<L, uint4>(dst, src, nbytes, lane); break;
         case 8: copy_vec<L, uint2>(dst, src, nbytes, lane); break;
@@ -153,297 +155,82 @@ template <int L> __device__ __forceinline__ void zero_bytes(void* dst, int nbyte
     }
 }
 
+// is_move_effective (ref :735-787): the literal window rule, evaluated by ONE lane with a virtual swap
+// (the board is not touched).  Used for hand-made / unstable boards and by the debug entry point.
+__device__ __noinline__ bool effective_literal(const int8_t* col, const int8_t* typ, int R, int C, int i1, int i2) {
+    const int ta = typ[i1], tb = typ[i2];
+    if (not01(ta) && not01(tb)) return true;             // ref :750
+    if (ta < 0 || tb < 0) return true;                   // ref :754
+    const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
+    const int rmin_ = max(0, min(r1, r2) - 2), rmax_ = min(R - 1, max(r1, r2) + 2);  // ref :758-761
+    const int cmin_ = max(0, min(c1, c2) - 2), cmax_ = min(C - 1, max(c1, c2) + 2);
+    auto cs = [&](int i) -> int { return i == i1 ? col[i2] : (i == i2 ? col[i1] : col[i]); };
+    auto ts = [&](int i) -> int { return i == i1 ? typ[i2] : (i == i2 ? typ[i1] : typ[i]); };
+    if (cmin_ + 2 <= cmax_)                               // ref :767-771
+        for (int r = rmin_; r <= rmax_; ++r)
+            for (int c = cmin_; c + 2 <= cmax_; ++c) {
+                const int i = r * C + c;
+                if (cs(i) == cs(i + 1) && cs(i + 1) == cs(i + 2) && ts(i + 2) >= 0) return true;
+            }
+    if (rmin_ + 2 <= rmax_)                               // ref :777-781
+        for (int r = rmin_; r + 2 <= rmax_; ++r)
+            for (int c = cmin_; c <= cmax_; ++c) {
+                const int i = r * C + c;
+                if (cs(i) == cs(i + C) && cs(i + C) == cs(i + 2 * C) && ts(i + 2 * C) >= 0) return true;
+            }
+    return false;
+}
+
+// literal per-action mask for one column (boards whose mask depends on the exact window rule; rare)
+struct MaskPair { unsigned v, h; };
+__device__ __noinline__ MaskPair mask_literal_column(const int8_t* col, const int8_t* typ, int R, int C, int lane) {
+    MaskPair o;
+    o.v = 0u; o.h = 0u;
+    if (lane < C)
+        for (int r = 0; r < R; ++r) {
+            const int i = r * C + lane;
+            if (r + 1 < R) o.v |= (unsigned)effective_literal(col, typ, R, C, i, i + C) << r;
+            if (lane + 1 < C) o.h |= (unsigned)effective_literal(col, typ, R, C, i, i + 1) << r;
+        }
+    return o;
+}
+
+// shuffle (ref :114-118): new[i] = old[perm[i]], perm = Fisher-Yates of arange(P) on stream 1.  Applying the
+// same swaps to the cells themselves yields exactly old[perm[i]].  One lane.
+__device__ __noinline__ void shuffle_serial(int8_t* col, int8_t* typ, int P, uint32_t gid, uint32_t key0, uint32_t key1,
+                                            uint64_t scur) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    uint64_t have_blk = ~0ull;
+    for (int i = P - 1; i >= 1; --i) {
+        const uint64_t k = scur++;
+        const uint64_t blk = k >> 2;
+        if (blk != have_blk) {
+            philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), gid, 1u, key0, key1, w);
+            have_blk = blk;
+        }
+        const uint32_t word = (k & 3) == 0 ? w[0] : (k & 3) == 1 ? w[1] : (k & 3) == 2 ? w[2] : w[3];
+        const int j = (int)__umulhi(word, (uint32_t)(i + 1));
+        const int8_t a = col[i], b = typ[i];
+        col[i] = col[j]; typ[i] = typ[j];
+        col[j] = a; typ[j] = b;
+    }
+}
+
 // ======================================================================================================
-// One board owned by a group of L lanes
+// Serial context: the order-dependent list semantics of the reference, run by the group's leader lane over
+// the shared-memory tables.  Kept out of line so the hot parallel code stays small.
 // ======================================================================================================
-template <int L> struct Board {
+template <int L> struct Serial {
     typedef Cfg<L> CF;
     GroupSmem<L>& s;
-    const Params& p;
-    const int lane;
-    const unsigned gmask;
-    const int gshift;
-    const int env;
-    const int R, C, P, K;
-    int8_t* const col;
-    int8_t* const typ;
-    uint64_t dcur, scur;
-    const uint32_t gid;
+    int8_t* col;
+    int8_t* typ;
+    int R, C, P;
+    uint32_t specials;
     uint32_t status;
-    int n_new, n_act;  // counters, meaningful on the leader lane (ref :343-344)
-    int nzc;           // leader: number of cells with colour != 0 while a serial section runs; -1 = unknown
+    int n_new, n_act;  // ref :343-344
+    int nzc;           // number of cells with colour != 0; -1 = not counted yet
 
-    __device__ Board(GroupSmem<L>& sm, const Params& pp, int lane_, unsigned gmask_, int gshift_, int env_)
-        : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(pp.R), C(pp.C), P(pp.P), K(pp.K),
-          col(sm.board), typ(sm.board + pp.P), dcur(0), scur(0), gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)),
-          status(0), n_new(0), n_act(0), nzc(-1) {}
-
-    // ---- group collectives ---------------------------------------------------------------------------
-    __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
-    __device__ __forceinline__ void sync(TMG_SITE_P0) const { TMG_SITE_SET __syncwarp(gmask); }
-    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, src, L); }
-    __device__ __forceinline__ unsigned shflu(unsigned v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, src, L); }
-    __device__ __forceinline__ int radd(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_add_sync(gmask, v); }
-    __device__ __forceinline__ int rmax(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_max_sync(gmask, v); }
-    __device__ __forceinline__ int rmin(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_min_sync(gmask, v); }
-    __device__ __forceinline__ unsigned ror(unsigned v TMG_SITE_P) const { TMG_SITE_SET return __reduce_or_sync(gmask, v); }
-    __device__ __forceinline__ unsigned lt_mask() const { return (1u << lane) - 1u; }
-    // neighbour-lane bitboards: value of lane+d / lane-d, 0 outside [0,L)
-    __device__ __forceinline__ unsigned from_right(unsigned v, int d TMG_SITE_P) const {
-        TMG_SITE_SET
-        const unsigned r = __shfl_down_sync(gmask, v, d, L);
-        return (lane + d < L) ? r : 0u;
-    }
-    __device__ __forceinline__ unsigned from_left(unsigned v, int d TMG_SITE_P) const {
-        TMG_SITE_SET
-        const unsigned r = __shfl_up_sync(gmask, v, d, L);
-        return (lane - d >= 0) ? r : 0u;
-    }
-
-    // ---- state I/O -----------------------------------------------------------------------------------
-    __device__ __forceinline__ void load_board(const int8_t* src, int vecw) {
-        copy_bytes<L>(s.board, src + (size_t)env * 2 * P, 2 * P, vecw, lane);
-        sync();
-    }
-    __device__ __forceinline__ void store_board() {
-        sync();
-        copy_bytes<L>(p.board + (size_t)env * 2 * P, s.board, 2 * P, p.board_vecw, lane);
-    }
-    __device__ __forceinline__ void store_mask() {
-        sync();
-        copy_bytes<L>(p.mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
-    }
-    __device__ __forceinline__ void store_zero_mask() { zero_bytes<L>(p.mask + (size_t)env * p.A, p.A, p.mask_vecw, lane); }
-    __device__ __forceinline__ void load_cursors() { dcur = p.draw_cursor[env]; scur = p.shuffle_cursor[env]; }
-    __device__ __forceinline__ void store_cursors() {
-        if (lane == 0) { p.draw_cursor[env] = dcur; p.shuffle_cursor[env] = scur; }
-    }
-
-    // ---- draw stream -----------------------------------------------------------------------------------
-    // words [start, start+n) of stream `stream` -> s.wbuf[0..n), n <= NW.  All lanes call.
-    __device__ __forceinline__ void fill_words(uint32_t stream, uint64_t start, int n) {
-        const uint64_t b0 = start >> 2;
-        const int nb = (int)(((start + (uint64_t)n - 1) >> 2) - b0) + 1;  // <= L because n <= 4(L-1)
-        if (lane < nb) {
-            const uint64_t b = b0 + (uint64_t)lane;
-            uint32_t w[4];
-            philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, stream, p.key0, p.key1, w);
-            const int base = (int)((long long)(b << 2) - (long long)start);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int idx = base + i;
-                if (idx >= 0 && idx < n) s.wbuf[idx] = w[i];
-            }
-        }
-        sync();
-    }
-    // colour of draw number `k` (relative to dcur) whose word sits at s.wbuf[widx]  (ref :97,129,239)
-    __device__ __forceinline__ int draw_colour(int k, int widx) {
-        if (p.use_inj) {
-            const long long q = (long long)dcur + k;
-            if (q < p.inj_len) return p.inj[(size_t)env * (size_t)p.inj_len + (size_t)q];
-            status |= ST_DRAWS_EXHAUSTED;
-            return 1;
-        }
-        return 1 + (int)__umulhi(s.wbuf[widx], (uint32_t)K);
-    }
-    // cells [0, n) in row-major order <- next n draws (initial fill ref :97 / row-block redraw ref :129)
-    __device__ void draw_cells(int n, bool set_type) {
-        sync();
-        for (int ps = 0; ps < n; ps += CF::NW) {
-            const int nw = min(CF::NW, n - ps);
-            if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
-            for (int i = lane; i < nw; i += L) {
-                col[ps + i] = (int8_t)draw_colour(ps + i, i);
-                if (set_type) typ[ps + i] = 1;
-            }
-            sync();
-        }
-        dcur += (uint64_t)n;
-    }
-
-    // ---- gravity (ref :217-229) + count of type==0 cells (ref :362,374) ------------------------------------
-    // returns the number of empty cells now on top of this lane's column; *elim gets P - count_nonzero(type)
-    __device__ int gravity(int* elim) {
-        sync();
-        int e = 0, nz = 0;
-        if (lane < C) {
-            int w = R - 1;
-            for (int r = R - 1; r >= 0; --r) {
-                const int i = r * C + lane;
-                const int x = col[i], t = typ[i];
-                nz += (t == 0);
-                if (x != 0 || t != 0) {
-                    if (w != r) { col[w * C + lane] = (int8_t)x; typ[w * C + lane] = (int8_t)t; }
-                    --w;
-                }
-            }
-            e = w + 1;
-            for (; w >= 0; --w) { col[w * C + lane] = 0; typ[w * C + lane] = 0; }
-        }
-        if (elim) *elim = radd(nz);
-        return e;
-    }
-
-    // ---- refill (ref :231-241): the k-th draw goes to the k-th empty cell in row-major order ---------------
-    __device__ void refill(int e) {
-        const int maxe = rmax(e);
-        if (maxe == 0) return;  // ref :238: no rng call when nothing is empty
-        const int total = radd(e);
-        const unsigned lt = lt_mask();
-        for (int ps = 0; ps < total; ps += CF::NW) {
-            const int nw = min(CF::NW, total - ps);
-            if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
-            int base = 0;
-            for (int r = 0; r < maxe; ++r) {
-                const unsigned m = ballot(e > r);
-                if (e > r) {
-                    const int rank = base + __popc(m & lt);
-                    if (rank >= ps && rank < ps + nw) {
-                        col[r * C + lane] = (int8_t)draw_colour(rank, rank - ps);
-                        typ[r * C + lane] = 1;
-                    }
-                }
-                base += __popc(m);
-            }
-            sync();
-        }
-        dcur += (uint64_t)total;
-    }
-
-    // ---- bottom-most line row (ref :158-193) -------------------------------------------------------------
-    struct Scan {
-        int rstar;        // row of the bottom-most anchored lines, -1 if the board has none
-        unsigned mv;      // lanes with a vertical line whose anchor (bottom) is at rstar
-        unsigned hs;      // start columns of the horizontal lines in row rstar
-        unsigned hcells;  // all cells of those horizontal lines
-        unsigned m;       // bit c: colour(rstar,c) == colour(rstar,c+1)
-        int vtop;         // per lane: top row of its vertical line
-        bool has_v;
-    };
-    __device__ Scan scan_lines(int from) {
-        Scan o;
-        o.rstar = -1; o.mv = o.hs = o.hcells = o.m = 0u; o.vtop = 0; o.has_v = false;
-        const bool in = lane < C;
-        for (int r = from; r >= 0; --r) {
-            int x = -1, t = 0, xr = -2;
-            bool v = false;
-            if (in) {
-                const int i = r * C + lane;
-                x = col[i];
-                t = typ[i];
-                if (lane + 1 < C) xr = col[i + 1];
-                if (r >= 2 && t > 0) v = (x == col[i - C]) && (x == col[i - 2 * C]);  // ref :163-173, anchor type only
-            }
-            const unsigned m = ballot(x == xr);
-            const unsigned T = ballot(t > 0);
-            const unsigned mv = ballot(v);
-            unsigned cand = m & (m >> 1) & T;  // anchors of horizontal triples with type > 0 (ref :179-181)
-            unsigned hs = 0u, hcells = 0u;
-            while (cand) {  // left to right; cells of a found line cannot anchor another (ref :179,192)
-                const int sidx = __ffs((int)cand) - 1;
-                const int run = __ffs((int)~(m >> sidx)) - 1;  // line = sidx .. sidx+run
-                const unsigned cells = ((2u << run) - 1u) << sidx;
-                hs |= 1u << sidx;
-                hcells |= cells;
-                cand &= ~cells;
-            }
-            if (mv | hs) {
-                o.rstar = r; o.mv = mv; o.hs = hs; o.hcells = hcells; o.m = m; o.has_v = v;
-                if (v) {
-                    int top = r - 2;
-                    while (top > 0 && col[(top - 1) * C + lane] == x) --top;  // ref :168-172
-                    o.vtop = top;
-                }
-                break;
-            }
-        }
-        return o;
-    }
-    // row of l[0][0] for the first line of get_colour_lines() (ref :127-128)
-    __device__ __forceinline__ int first_line_top(const Scan& sc) {
-        const int cv = sc.mv ? __ffs((int)sc.mv) - 1 : 64;
-        const int ch = sc.hs ? __ffs((int)sc.hs) - 1 : 64;
-        const int vt = shfl(sc.vtop, cv < 64 ? cv : 0);
-        return (cv <= ch) ? vt : sc.rstar;  // vertical is listed before horizontal at the same column (ref :163,179)
-    }
-
-    // ---- line table in the reference's list order (ref :149-215, closed form in SURVEY.md A.4) -------------
-    // returns the number of lines; s.order holds them sorted for process_colour_lines (ref :282)
-    __device__ int build_line_table(const Scan& sc) {
-        const int rs = sc.rstar;
-        const unsigned lt = lt_mask();
-        // phase 1: by column, vertical before horizontal
-        const int before = __popc(sc.mv & lt) + __popc(sc.hs & lt);
-        int n = __popc(sc.mv) + __popc(sc.hs);
-        if (sc.has_v) {
-            const int slot = before;
-            if (slot < CF::ML) {
-                const int len = rs - sc.vtop + 1;
-                for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)((sc.vtop + k) * C + lane);
-                s.line_len[slot] = (uint8_t)len;
-                s.line_colour[slot] = (uint8_t)col[rs * C + lane];
-                s.line_key[slot] = ((uint32_t)sc.vtop << 12) | (uint32_t)slot;
-            }
-        }
-        if ((sc.hs >> lane) & 1u) {
-            const int slot = before + (sc.has_v ? 1 : 0);
-            if (slot < CF::ML) {
-                const int run = __ffs((int)~(sc.m >> lane)) - 1;
-                for (int k = 0; k <= run; ++k) s.line_cells[slot][k] = (uint16_t)(rs * C + lane + k);
-                s.line_len[slot] = (uint8_t)(run + 1);
-                s.line_colour[slot] = (uint8_t)col[rs * C + lane];
-                s.line_key[slot] = ((uint32_t)rs << 12) | (uint32_t)slot;
-            }
-        }
-        // phase 2 (ref :198-214): horizontal segments through the cells of the vertical lines, cut at phase-1 cells
-        if (sc.mv) {
-            const int rmin_ = rmin(sc.has_v ? sc.vtop : 1 << 20);
-            for (int r = rmin_; r <= rs; ++r) {
-                int x = -1, t = 0, xr = -2;
-                if (lane < C) {
-                    x = col[r * C + lane];
-                    t = typ[r * C + lane];
-                    if (lane + 1 < C) xr = col[r * C + lane + 1];
-                }
-                const unsigned m = ballot(x == xr);
-                const unsigned T = ballot(t > 0);
-                const bool origin = sc.has_v && sc.vtop <= r;
-                unsigned Q = ballot(origin);
-                if (r == rs) Q |= sc.hcells;
-                const unsigned pass = T & ~Q;
-                int left = 0, right = 0;
-                bool seg = false;
-                if (origin && t > 0) {  // match_color needs type > 0 on both cells (ref :199)
-                    const unsigned chain_r = (m << 1) & pass;  // bit j: cell j equals cell j-1 and may be entered
-                    const unsigned chain_l = m & pass;         // bit j: cell j equals cell j+1 and may be entered
-                    if (lane + 1 < L) right = __ffs((int)~(chain_r >> (lane + 1))) - 1;
-                    if (lane > 0) left = __clz((int)~(chain_l << (32 - lane)));
-                    seg = (1 + left + right) >= 3;
-                }
-                const unsigned segm = ballot(seg);
-                if (seg) {
-                    const int slot = n + __popc(segm & lt);
-                    if (slot < CF::ML) {
-                        const int len = 1 + left + right;
-                        for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)(r * C + lane - left + k);
-                        s.line_len[slot] = (uint8_t)len;
-                        s.line_colour[slot] = (uint8_t)x;
-                        // same top row: phase 1 first, then phase 2 by (column of the vertical line, row)
-                        s.line_key[slot] = ((uint32_t)r << 12) | (uint32_t)(1024 + lane * 32 + r);
-                    }
-                }
-                n += __popc(segm);
-            }
-        }
-        if (n > CF::ML) { status |= ST_LINE_OVERFLOW; n = CF::ML; }
-        sync();
-        return n;
-    }
-
-    // ===================================================================================================
-    // Serial (leader-lane) part: exact list semantics
-    // ===================================================================================================
     __device__ __forceinline__ void del_cell(int i) {
         if (nzc >= 0 && col[i] != 0) --nzc;
         col[i] = 0;
@@ -454,7 +241,6 @@ template <int L> struct Board {
         for (int i = 0; i < P; ++i) n += (col[i] != 0);
         nzc = n;
     }
-
     // frame: kind(2) | cell(10) << 2 | cursor(11) << 12 | colour(5) << 23
     __device__ __forceinline__ static uint32_t frame(int kind, int cell, int cursor, int mc) {
         return (uint32_t)kind | ((uint32_t)cell << 2) | ((uint32_t)cursor << 12) | ((uint32_t)mc << 23);
@@ -477,13 +263,13 @@ template <int L> struct Board {
             for (int i = 0; i < P; ++i) { const int x = col[i]; if (x > 0 && x < 32) ++s.cnt[x]; }
             int best = 0;
             for (int k = 1; k < 32; ++k) if (s.cnt[k] > best) { best = s.cnt[k]; mc = k; }  // ref :536-537
-            for (int i = 0; i < P; ++i) if (col[i] == mc && typ[i] == 1) del_cell(i);                 // ref :540-544
+            for (int i = 0; i < P; ++i) if (col[i] == mc && typ[i] == 1) del_cell(i);       // ref :540-544
         } else { status |= ST_INTERNAL; return; }  // ref :555-556 raises
         if (sp >= CF::DFS) { status |= ST_DFS_OVERFLOW; return; }
         s.stack[sp++] = frame(kind, cell, 0, mc);
     }
     // activate_special (ref :473-556) as an explicit-stack DFS that re-reads live cells in the reference's order
-    __device__ void activate(int cell0, int t0, bool counted) {
+    __device__ __noinline__ void activate(int cell0, int t0, bool counted) {
         int sp = 0;
         enter_activation(cell0, t0, counted, sp);
         while (sp > 0) {
@@ -518,7 +304,7 @@ template <int L> struct Board {
     }
 
     // get_special_creation_pos (ref :429-458) on s.match[0..n)
-    __device__ int creation_pos(int n, int ntaken, bool straight) {
+    __device__ __noinline__ int creation_pos(int n, int ntaken, bool straight) {
         auto is_taken = [&](int cell) {
             for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
             return false;
@@ -560,7 +346,8 @@ template <int L> struct Board {
     // process_colour_lines (ref :269-327) fused with resolve_colour_matches (ref :397-427): the creation cell
     // of a match depends only on coordinates, so each match is resolved as soon as it is classified; the new
     // specials are written after all deletions, as in the reference.
-    __device__ void process_and_resolve(int n) {
+    __device__ __noinline__ void process_and_resolve(int n) {
+        nzc = -1;
         // ref :282: stable sort by the first cell's row == sort by key (keys are unique)
         for (int i = 0; i < n; ++i) s.order[i] = (uint8_t)i;
         for (int i = 1; i < n; ++i) {
@@ -571,8 +358,8 @@ template <int L> struct Board {
             s.order[j + 1] = v;
         }
         int qh = 0, qn = n, nslots = n, ncq = 0, ntaken = 0;
-        const bool sp_cookie = p.specials & SP_COOKIE, sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER,
-                   sp_bomb = p.specials & SP_BOMB;
+        const bool sp_cookie = specials & SP_COOKIE, sp_v = specials & SP_VLASER, sp_h = specials & SP_HLASER,
+                   sp_bomb = specials & SP_BOMB;
         while (qh < qn) {
             const int li = s.order[qh++];                    // ref :285 pop(0)
             const int len = s.line_len[li];
@@ -668,22 +455,11 @@ template <int L> struct Board {
         }
     }
 
-    // one cascade round without gravity/refill (ref :369-373); returns the number of lines found
-    __device__ int resolve_round(int from) {
-        sync();
-        const Scan sc = scan_lines(from);
-        if (sc.rstar < 0) return 0;
-        const int n = build_line_table(sc);
-        if (lane == 0) { nzc = -1; process_and_resolve(n); }
-        sync();
-        return n;
-    }
-
-    // combination_match (ref :600-719), leader lane
-    __device__ void combination(int i1, int i2) {
+    // combination_match (ref :600-719)
+    __device__ __noinline__ void combination(int i1, int i2) {
         n_act += 2;                                          // ref :609
         nzc = -1;
-        int t1 = typ[i1], k1 = col[i1], t2 = typ[i2], k2 = col[i2];
+        const int t1 = typ[i1], k1 = col[i1], t2 = typ[i2], k2 = col[i2];
         const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
         if (t1 == -1 && t2 == -1) {                          // ref :615-616
             for (int i = 0; i < P; ++i) { col[i] = 0; typ[i] = 0; }
@@ -702,8 +478,7 @@ template <int L> struct Board {
             const int tt = (t1 == -1) ? t2 : t1;
             del_cell(ck);                                    // ref :651
             // ref :654 snapshot of colour==kk; a cell leaves the snapshot only by deletion (colour -> 0), and a cell
-            // that was not in it never gains the colour, so a live test of colour==kk is the same set.  kk == 0 would
-            // also select emptied cells, but their type is 0 and they are skipped either way.
+            // that was not in it never gains the colour, so a live test of colour==kk is the same set.
             for (int i = 0; i < P; ++i) if (col[i] == kk && typ[i] == 1) typ[i] = (int8_t)tt;  // ref :655-657
             for (int i = 0; i < P; ++i)
                 if (col[i] == kk && not01(typ[i])) activate(i, typ[i], false);                 // ref :660
@@ -732,37 +507,347 @@ template <int L> struct Board {
                 }
         }
     }
+};
 
-    // shuffle (ref :114-118): new[i] = old[perm[i]], perm = Fisher-Yates of arange(P) on stream 1.  Applying the
-    // same swaps to the cells themselves yields exactly old[perm[i]].  Leader lane.
-    __device__ void shuffle_serial() {
-        uint32_t w[4];
-        uint64_t have_blk = ~0ull;
-        for (int i = P - 1; i >= 1; --i) {
-            const uint64_t k = scur++;
-            const uint64_t blk = k >> 2;
-            if (blk != have_blk) {
-                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), gid, 1u, p.key0, p.key1, w);
-                have_blk = blk;
-            }
-            const uint32_t word = (k & 3) == 0 ? w[0] : (k & 3) == 1 ? w[1] : (k & 3) == 2 ? w[2] : w[3];
-            const int j = (int)__umulhi(word, (uint32_t)(i + 1));
-            const int8_t a = col[i], b = typ[i];
-            col[i] = col[j]; typ[i] = typ[j];
-            col[j] = a; typ[j] = b;
-        }
+// ======================================================================================================
+// One board owned by a group of L lanes
+// ======================================================================================================
+template <int L> struct Board {
+    typedef Cfg<L> CF;
+    GroupSmem<L>& s;
+    const Params& p;
+    const int lane;
+    const unsigned gmask;
+    const int gshift;
+    const int env;
+    const int R, C, P, K;
+    int8_t* const col;
+    int8_t* const typ;
+    uint64_t dcur, scur;
+    const uint32_t gid;
+    uint32_t status;
+    int n_new, n_act;  // counters, uniform after broadcast (ref :343-344)
+    uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
+
+    __device__ Board(GroupSmem<L>& sm, const Params& pp, int lane_, unsigned gmask_, int gshift_, int env_)
+        : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(pp.R), C(pp.C), P(pp.P), K(pp.K),
+          col(sm.board), typ(sm.board + pp.P), dcur(0), scur(0), gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)),
+          status(0), n_new(0), n_act(0) {}
+
+    // ---- group collectives ---------------------------------------------------------------------------
+    __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
+    __device__ __forceinline__ void sync(TMG_SITE_P0) const { TMG_SITE_SET __syncwarp(gmask); }
+    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, src, L); }
+    __device__ __forceinline__ int radd(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_add_sync(gmask, v); }
+    __device__ __forceinline__ int rmax(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_max_sync(gmask, v); }
+    __device__ __forceinline__ int rmin(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_min_sync(gmask, v); }
+    __device__ __forceinline__ unsigned ror(unsigned v TMG_SITE_P) const { TMG_SITE_SET return __reduce_or_sync(gmask, v); }
+    __device__ __forceinline__ unsigned lt_mask() const { return (1u << lane) - 1u; }
+    // neighbour-lane bitboards: value of lane+d / lane-d, 0 outside [0,L)
+    __device__ __forceinline__ unsigned from_right(unsigned v, int d TMG_SITE_P) const {
+        TMG_SITE_SET
+        const unsigned r = __shfl_down_sync(gmask, v, d, L);
+        return (lane + d < L) ? r : 0u;
     }
+    __device__ __forceinline__ unsigned from_left(unsigned v, int d TMG_SITE_P) const {
+        TMG_SITE_SET
+        const unsigned r = __shfl_up_sync(gmask, v, d, L);
+        return (lane - d >= 0) ? r : 0u;
+    }
+    __device__ __forceinline__ unsigned rows_mask() const { return R >= 32 ? 0xffffffffu : ((1u << R) - 1u); }
+
+    // ---- state I/O -----------------------------------------------------------------------------------
+    __device__ __forceinline__ void load_board(const int8_t* src, int vecw) {
+        copy_bytes<L>(s.board, src + (size_t)env * 2 * P, 2 * P, vecw, lane);
+        sync();
+    }
+    __device__ __forceinline__ void store_board() {
+        sync();
+        copy_bytes<L>(p.board + (size_t)env * 2 * P, s.board, 2 * P, p.board_vecw, lane);
+    }
+    __device__ __forceinline__ void store_mask() {
+        sync();
+        copy_bytes<L>(p.mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
+    }
+    __device__ __forceinline__ void store_zero_mask() { zero_bytes<L>(p.mask + (size_t)env * p.A, p.A, p.mask_vecw, lane); }
+    __device__ __forceinline__ void load_cursors() { dcur = p.draw_cursor[env]; scur = p.shuffle_cursor[env]; }
+    __device__ __forceinline__ void store_cursors() {
+        if (lane == 0) { p.draw_cursor[env] = dcur; p.shuffle_cursor[env] = scur; }
+    }
+
+    // ---- draw stream -----------------------------------------------------------------------------------
+    // words [start, start+n) of stream `stream` -> s.wbuf[0..n), n <= NW.  All lanes call.
+    __device__ __forceinline__ void fill_words(uint32_t stream, uint64_t start, int n) {
+        const uint64_t b0 = start >> 2;
+        const int nb = (int)(((start + (uint64_t)n - 1) >> 2) - b0) + 1;  // <= L because n <= 4(L-1)
+        if (lane < nb) {
+            const uint64_t b = b0 + (uint64_t)lane;
+            uint32_t w[4];
+            philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, stream, p.key0, p.key1, w);
+            const int base = (int)((long long)(b << 2) - (long long)start);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = base + i;
+                if (idx >= 0 && idx < n) s.wbuf[idx] = w[i];
+            }
+        }
+        sync();
+    }
+    __device__ __forceinline__ int injected_colour(int k) {
+        const long long q = (long long)dcur + k;
+        if (q < p.inj_len) return p.inj[(size_t)env * (size_t)p.inj_len + (size_t)q];
+        status |= ST_DRAWS_EXHAUSTED;
+        return 1;
+    }
+    // cells [0, n) in row-major order <- next n draws (initial fill ref :97 / row-block redraw ref :129).
+    // Cell i takes word dcur+i, so each lane turns whole Philox blocks straight into board bytes.
+    __device__ void draw_cells(int n, bool set_type) {
+        sync();
+        if (set_type) {
+            uint32_t* t32 = reinterpret_cast<uint32_t*>(s.board);  // type plane may start unaligned: bytes at the edges
+            (void)t32;
+            for (int i = lane; i < n; i += L) typ[i] = 1;
+        }
+        if (p.use_inj) {
+            for (int i = lane; i < n; i += L) col[i] = (int8_t)injected_colour(i);
+        } else {
+            const uint64_t b0 = dcur >> 2, b1 = (dcur + (uint64_t)n - 1) >> 2;
+            for (uint64_t b = b0 + (uint64_t)lane; b <= b1; b += L) {
+                uint32_t w[4];
+                philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, 0u, p.key0, p.key1, w);
+                const int base = (int)((long long)(b << 2) - (long long)dcur);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int idx = base + i;
+                    if (idx >= 0 && idx < n) col[idx] = (int8_t)(1 + (int)__umulhi(w[i], (uint32_t)K));
+                }
+            }
+        }
+        dcur += (uint64_t)n;
+        sync();
+    }
+
+    // ---- gravity (ref :217-229) + count of type==0 cells (ref :362,374) ------------------------------------
+    // returns the number of empty cells now on top of this lane's column; *elim gets P - count_nonzero(type)
+    __device__ int gravity(int* elim) {
+        sync();
+        int e = 0, nz = 0;
+        if (lane < C) {
+            int w = R - 1;
+            for (int r = R - 1; r >= 0; --r) {
+                const int i = r * C + lane;
+                const int x = col[i], t = typ[i];
+                nz += (t == 0);
+                if (x != 0 || t != 0) {
+                    if (w != r) { col[w * C + lane] = (int8_t)x; typ[w * C + lane] = (int8_t)t; }
+                    --w;
+                }
+            }
+            e = w + 1;
+            for (; w >= 0; --w) { col[w * C + lane] = 0; typ[w * C + lane] = 0; }
+        }
+        if (elim) *elim = radd(nz);
+        return e;
+    }
+
+    // ---- refill (ref :231-241): the k-th draw goes to the k-th empty cell in row-major order ---------------
+    __device__ void refill(int e) {
+        const int maxe = rmax(e);
+        if (maxe == 0) return;  // ref :238: no rng call when nothing is empty
+        const int total = radd(e);
+        const unsigned lt = lt_mask();
+        for (int ps = 0; ps < total; ps += CF::NW) {
+            const int nw = min(CF::NW, total - ps);
+            if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
+            int base = 0;
+            for (int r = 0; r < maxe; ++r) {
+                const unsigned m = ballot(e > r);
+                if (e > r) {
+                    const int rank = base + __popc(m & lt);
+                    if (rank >= ps && rank < ps + nw) {
+                        col[r * C + lane] = (int8_t)(p.use_inj ? injected_colour(rank)
+                                                               : 1 + (int)__umulhi(s.wbuf[rank - ps], (uint32_t)K));
+                        typ[r * C + lane] = 1;
+                    }
+                }
+                base += __popc(m);
+            }
+            sync();
+        }
+        dcur += (uint64_t)total;
+    }
+
+    // ---- line detection (ref :149-215) ---------------------------------------------------------------------
+    // Per-lane row bitboards of column c: E bit r: colour(r,c)==colour(r,c+1); D bit r: colour(r,c)==colour(r-1,c);
+    // T bit r: type(r,c) > 0.  One pass over the column finds every anchored line of the board at once.
+    struct Bits { unsigned E, D, T; };
+    __device__ __forceinline__ Bits column_bits(bool all_normal) const {
+        Bits b;
+        b.E = b.D = b.T = 0u;
+        if (lane < C) {
+            int prev = -3;
+            const bool has_right = lane + 1 < C;
+#pragma unroll 4
+            for (int r = 0; r < R; ++r) {
+                const int i = r * C + lane;
+                const int x = col[i];
+                const int xr = has_right ? (int)col[i + 1] : -2;
+                b.E |= (unsigned)(x == xr) << r;
+                b.D |= (unsigned)(x == prev) << r;
+                if (!all_normal) b.T |= (unsigned)(typ[i] > 0) << r;
+                prev = x;
+            }
+            if (all_normal) b.T = rows_mask();
+        }
+        return b;
+    }
+    struct Scan {
+        int rstar;        // row of the bottom-most anchored lines, -1 if the board has none (ref :158-160)
+        unsigned mv;      // lanes with a vertical line whose anchor (bottom) is at rstar
+        unsigned hs;      // start columns of the horizontal lines in row rstar
+        unsigned hcells;  // all cells of those horizontal lines
+        unsigned m;       // bit c: colour(rstar,c) == colour(rstar,c+1)
+        int vtop;         // per lane: top row of its vertical line
+        bool has_v;
+        Bits bits;
+    };
+    // rows above `from` are known to be line-free
+    __device__ Scan scan_lines(int from, bool all_normal) {
+        Scan o;
+        o.bits = column_bits(all_normal);
+        const Bits& b = o.bits;
+        const unsigned V = b.D & (b.D << 1) & b.T;            // vertical triple anchored (bottom) at r, anchor type > 0 (ref :163-173)
+        const unsigned H = b.E & from_right(b.E, 1) & b.T;    // horizontal triple anchored (left) at (r,c)   (ref :179-189)
+        const unsigned lim = (from >= 31) ? 0xffffffffu : ((2u << from) - 1u);
+        const unsigned F = (V | H) & lim;
+        o.rstar = rmax(F ? 31 - __clz((int)F) : -1);
+        o.mv = o.hs = o.hcells = o.m = 0u; o.vtop = 0; o.has_v = false;
+        if (o.rstar < 0) return o;
+        const int rs = o.rstar;
+        const unsigned m = ballot((b.E >> rs) & 1u);
+        const unsigned T = ballot((b.T >> rs) & 1u);
+        o.has_v = (V >> rs) & 1u;
+        o.mv = ballot(o.has_v);
+        unsigned cand = m & (m >> 1) & T, hs = 0u, hcells = 0u;
+        while (cand) {  // left to right; cells of a found line cannot anchor another (ref :179,192)
+            const int sidx = __ffs((int)cand) - 1;
+            const int run = __ffs((int)~(m >> sidx)) - 1;  // line = sidx .. sidx+run
+            const unsigned cells = ((2u << run) - 1u) << sidx;
+            hs |= 1u << sidx;
+            hcells |= cells;
+            cand &= ~cells;
+        }
+        o.hs = hs; o.hcells = hcells; o.m = m;
+        if (o.has_v) o.vtop = rs - __clz((int)~(b.D << (31 - rs)));  // extend upwards while equal (ref :168-172)
+        return o;
+    }
+    // row of l[0][0] for the first line of get_colour_lines() (ref :127-128)
+    __device__ __forceinline__ int first_line_top(const Scan& sc) {
+        const int cv = sc.mv ? __ffs((int)sc.mv) - 1 : 64;
+        const int ch = sc.hs ? __ffs((int)sc.hs) - 1 : 64;
+        const int vt = shfl(sc.vtop, cv < 64 ? cv : 0);
+        return (cv <= ch) ? vt : sc.rstar;  // vertical is listed before horizontal at the same column (ref :163,179)
+    }
+
+    // ---- line table in the reference's list order (closed form in SURVEY.md A.4) ---------------------------
+    // returns the number of lines; keys give the processing order of process_colour_lines (ref :282)
+    __device__ int build_line_table(const Scan& sc) {
+        const int rs = sc.rstar;
+        const unsigned lt = lt_mask();
+        // phase 1: by column, vertical before horizontal
+        const int before = __popc(sc.mv & lt) + __popc(sc.hs & lt);
+        int n = __popc(sc.mv) + __popc(sc.hs);
+        if (sc.has_v) {
+            const int slot = before;
+            if (slot < CF::ML) {
+                const int len = rs - sc.vtop + 1;
+                for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)((sc.vtop + k) * C + lane);
+                s.line_len[slot] = (uint8_t)len;
+                s.line_colour[slot] = (uint8_t)col[rs * C + lane];
+                s.line_key[slot] = ((uint32_t)sc.vtop << 12) | (uint32_t)slot;
+            }
+        }
+        if ((sc.hs >> lane) & 1u) {
+            const int slot = before + (sc.has_v ? 1 : 0);
+            if (slot < CF::ML) {
+                const int run = __ffs((int)~(sc.m >> lane)) - 1;
+                for (int k = 0; k <= run; ++k) s.line_cells[slot][k] = (uint16_t)(rs * C + lane + k);
+                s.line_len[slot] = (uint8_t)(run + 1);
+                s.line_colour[slot] = (uint8_t)col[rs * C + lane];
+                s.line_key[slot] = ((uint32_t)rs << 12) | (uint32_t)slot;
+            }
+        }
+        // phase 2 (ref :198-214): horizontal segments through the cells of the vertical lines, cut at phase-1 cells
+        if (sc.mv) {
+            const int rmin_ = rmin(sc.has_v ? sc.vtop : 1 << 20);
+            for (int r = rmin_; r <= rs; ++r) {
+                const unsigned m = ballot((sc.bits.E >> r) & 1u);
+                const unsigned T = ballot((sc.bits.T >> r) & 1u);
+                const bool origin = sc.has_v && sc.vtop <= r;
+                unsigned Q = ballot(origin);
+                if (r == rs) Q |= sc.hcells;
+                const unsigned pass = T & ~Q;
+                int left = 0, right = 0;
+                bool seg = false;
+                if (origin && ((sc.bits.T >> r) & 1u)) {  // match_color needs type > 0 on both cells (ref :199)
+                    const unsigned chain_r = (m << 1) & pass;  // bit j: cell j equals cell j-1 and may be entered
+                    const unsigned chain_l = m & pass;         // bit j: cell j equals cell j+1 and may be entered
+                    if (lane + 1 < L) right = __ffs((int)~(chain_r >> (lane + 1))) - 1;
+                    if (lane > 0) left = __clz((int)~(chain_l << (32 - lane)));
+                    seg = (1 + left + right) >= 3;
+                }
+                const unsigned segm = ballot(seg);
+                if (seg) {
+                    const int slot = n + __popc(segm & lt);
+                    if (slot < CF::ML) {
+                        const int len = 1 + left + right;
+                        for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)(r * C + lane - left + k);
+                        s.line_len[slot] = (uint8_t)len;
+                        s.line_colour[slot] = (uint8_t)col[r * C + lane];
+                        // same top row: phase 1 first, then phase 2 by (column of the vertical line, row)
+                        s.line_key[slot] = ((uint32_t)r << 12) | (uint32_t)(1024 + lane * 32 + r);
+                    }
+                }
+                n += __popc(segm);
+            }
+        }
+        if (n > CF::ML) { status |= ST_LINE_OVERFLOW; n = CF::ML; }
+        sync();
+        return n;
+    }
+
+    // ---- leader-lane serial sections ---------------------------------------------------------------------
+    __device__ __forceinline__ Serial<L> make_serial() {
+        Serial<L> q{s, col, typ, R, C, P, p.specials, 0u, n_new, n_act, -1};
+        return q;
+    }
+    __device__ __forceinline__ void take_serial(const Serial<L>& q) { status |= q.status; n_new = q.n_new; n_act = q.n_act; }
+
+    // one cascade round without gravity/refill (ref :369-373); returns the number of lines found
+    __device__ int resolve_round() {
+        sync();
+        const Scan sc = scan_lines(R - 1, false);
+        if (sc.rstar < 0) return 0;
+        const int n = build_line_table(sc);
+        ++prof_rounds;
+        if (lane == 0) {
+            const long long t0 = p.prof ? clock64() : 0;
+            Serial<L> q = make_serial();
+            q.process_and_resolve(n);
+            take_serial(q);
+            if (p.prof) prof_serial += (uint32_t)(clock64() - t0);
+        }
+        sync();
+        return n;
+    }
+
     __device__ void shuffle() {
         sync();
-        const uint64_t s0 = scur;
-        if (lane == 0) shuffle_serial();
-        scur = s0 + (uint64_t)(P > 1 ? P - 1 : 0);  // one word per Fisher-Yates step, on every lane
+        if (lane == 0) shuffle_serial(col, typ, P, gid, p.key0, p.key1, scur);
+        scur += (uint64_t)(P > 1 ? P - 1 : 0);  // one word per Fisher-Yates step, on every lane
         sync();
     }
 
-    // ===================================================================================================
-    // is_move_effective (ref :735-787)
-    // ===================================================================================================
     __device__ __forceinline__ void action_cells(int a, int& i1, int& i2) const {  // ref :80-91
         const int nv = C * (R - 1);
         if (a < nv) { i1 = a; i2 = a + C; }
@@ -772,31 +857,8 @@ template <int L> struct Board {
             i1 = r * C + c; i2 = i1 + 1;
         }
     }
-    // literal window rule, evaluated by ONE lane with a virtual swap (the board is not touched)
-    __device__ bool effective_literal(int i1, int i2) const {
-        const int ta = typ[i1], tb = typ[i2];
-        if (not01(ta) && not01(tb)) return true;             // ref :750
-        if (ta < 0 || tb < 0) return true;                   // ref :754
-        const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
-        const int rmin_ = max(0, min(r1, r2) - 2), rmax_ = min(R - 1, max(r1, r2) + 2);  // ref :758-761
-        const int cmin_ = max(0, min(c1, c2) - 2), cmax_ = min(C - 1, max(c1, c2) + 2);
-        auto cs = [&](int i) -> int { return i == i1 ? col[i2] : (i == i2 ? col[i1] : col[i]); };
-        auto ts = [&](int i) -> int { return i == i1 ? typ[i2] : (i == i2 ? typ[i1] : typ[i]); };
-        if (cmin_ + 2 <= cmax_)                               // ref :767-771
-            for (int r = rmin_; r <= rmax_; ++r)
-                for (int c = cmin_; c + 2 <= cmax_; ++c) {
-                    const int i = r * C + c;
-                    if (cs(i) == cs(i + 1) && cs(i + 1) == cs(i + 2) && ts(i + 2) >= 0) return true;
-                }
-        if (rmin_ + 2 <= rmax_)                               // ref :777-781
-            for (int r = rmin_; r + 2 <= rmax_; ++r)
-                for (int c = cmin_; c <= cmax_; ++c) {
-                    const int i = r * C + c;
-                    if (cs(i) == cs(i + C) && cs(i + C) == cs(i + 2 * C) && ts(i + 2 * C) >= 0) return true;
-                }
-        return false;
-    }
-    // one action, all lanes cooperate: lane j tests window row j (horizontal triples) and window column j (vertical)
+    // is_move_effective for one action, all lanes cooperate: lane j tests window row j (horizontal triples) and
+    // window column j (vertical triples) with a virtual swap (ref :735-787)
     __device__ bool effective_group(int a) {
         int i1, i2;
         action_cells(a, i1, i2);
@@ -828,14 +890,14 @@ template <int L> struct Board {
     // legal-move mask (ref tile_match_env.py:118-124) by row bitboards: lane c holds, per colour k, the set of
     // rows of column c that carry k.  effv bit r <-> action r*C+c (swap with the cell below);
     // effh bit r <-> action C(R-1) + r(C-1) + c (swap with the cell to the right).
-    // Boards with a pre-existing triple inside some window, or with a coloured tile of negative type, take the
+    // Boards with a pre-existing triple, or with a cell whose (colour==0) disagrees with (type<0), take the
     // literal per-action path (their masks depend on the exact window rule).
     // ===================================================================================================
-    __device__ void mask_bits(unsigned& effv, unsigned& effh, bool& any) {
+    __device__ __forceinline__ bool mask_bits(unsigned& effv_out, unsigned& effh_out) {
         sync();
         const bool in = lane < C;
         unsigned S = 0u, Ng = 0u;    // rows with type not in {0,1} / type < 0
-        bool odd = false;            // coloured tile with negative type, or colour 0 with type >= 0
+        bool odd = false;
         if (in)
             for (int r = 0; r < R; ++r) {
                 const int t = typ[r * C + lane], x = col[r * C + lane];
@@ -843,9 +905,10 @@ template <int L> struct Board {
                 Ng |= (unsigned)(t < 0) << r;
                 odd |= (t < 0) != (x == 0);
             }
-        const unsigned rows_v = (R >= 32 ? 0xffffffffu : ((1u << R) - 1u)) >> 1;  // rows r with r+1 < R
-        effv = ((S & (S >> 1)) | Ng | (Ng >> 1)) & rows_v;                        // ref :750,754
-        effh = (S & from_right(S, 1)) | Ng | from_right(Ng, 1);
+        const unsigned rows = rows_mask();
+        const unsigned rows_v = rows >> 1;  // rows r with r+1 < R
+        unsigned effv = ((S & (S >> 1)) | Ng | (Ng >> 1));                       // ref :750,754
+        unsigned effh = (S & from_right(S, 1)) | Ng | from_right(Ng, 1);
         unsigned unstable = 0u;
         for (int k = 1; k <= K; ++k) {
             unsigned b = 0u;
@@ -864,17 +927,13 @@ template <int L> struct Board {
         if (!in || lane + 1 >= C) effh = 0u;
         if (!in) effv = 0u;
         effv &= rows_v;
-        effh &= (R >= 32 ? 0xffffffffu : ((1u << R) - 1u));
-        if (ballot(unstable != 0u || odd)) {  // literal window rule, one action at a time per lane (rare)
-            effv = 0u; effh = 0u;
-            if (in)
-                for (int r = 0; r < R; ++r) {
-                    const int i = r * C + lane;
-                    if (r + 1 < R) effv |= (unsigned)effective_literal(i, i + C) << r;
-                    if (lane + 1 < C) effh |= (unsigned)effective_literal(i, i + 1) << r;
-                }
+        effh &= rows;
+        if (ballot(unstable != 0u || odd)) {
+            const MaskPair lit = mask_literal_column(col, typ, R, C, lane);
+            effv = lit.v; effh = lit.h;
         }
-        any = ballot((effv | effh) != 0u) != 0u;
+        effv_out = effv; effh_out = effh;
+        return ballot((effv | effh) != 0u) != 0u;
     }
     __device__ void mask_to_smem(unsigned effv, unsigned effh) {
         if (lane < C) {
@@ -889,48 +948,46 @@ template <int L> struct Board {
     // ===================================================================================================
     // playability loop shared by generate_board (ref :99-109) and move (ref :381-391)
     // ===================================================================================================
-    // `clean`: the caller knows the board has no lines.  Leaves the mask bits of the final board in effv/effh.
-    __device__ bool playability(bool clean, unsigned& effv, unsigned& effh) {
+    // `clean`: the caller knows the board has no lines.  `all_normal`: every tile has type 1 (fresh board).
+    // Leaves the mask bits of the final board in effv/effh.
+    __device__ __forceinline__ bool playability(bool clean, bool all_normal, unsigned& effv, unsigned& effh) {
         bool shuffled = false;
         int iters = 0, from = R - 1;
+#pragma unroll 1
         for (;;) {
+            bool capped = false;
             if (!clean) {
                 sync();
-                const Scan sc = scan_lines(from);
+                const Scan sc = scan_lines(from, all_normal);
                 if (sc.rstar >= 0) {                         // remove_colour_lines (ref :120-131)
-                    if (iters >= p.max_iters) { status |= ST_RESET_CAP; break; }
-                    ++iters;
-                    const int top = first_line_top(sc);
-                    const int row = min(R - 1, top + 1);
-                    draw_cells((row + 1) * C, false);
-                    // rows below max(rstar, row+2) were line-free before and none of their 3-windows changed
-                    from = min(R - 1, max(sc.rstar, row + 2));
-                    continue;
+                    if (iters < p.max_iters) {
+                        ++iters;
+                        ++prof_iters;
+                        const int top = first_line_top(sc);
+                        const int row = min(R - 1, top + 1);
+                        draw_cells((row + 1) * C, false);
+                        // rows below max(rstar, row+2) were line-free before and none of their 3-windows changed
+                        from = min(R - 1, max(sc.rstar, row + 2));
+                        continue;
+                    }
+                    status |= ST_RESET_CAP;
+                    capped = true;
                 }
             }
-            bool any;
-            mask_bits(effv, effh, any);
-            if (any) return shuffled;                        // possible_move (ref :558-569)
+            const bool any = mask_bits(effv, effh);          // possible_move (ref :558-569)
+            if (any || capped) return shuffled;
             if (iters >= p.max_iters) { status |= ST_RESET_CAP; return shuffled; }
             ++iters;
             shuffled = true;
             shuffle();
             clean = false;
+            all_normal = false;
             from = R - 1;
         }
-        bool any;
-        mask_bits(effv, effh, any);
-        return shuffled;
     }
 
-    // generate_board (ref :95-112)
-    __device__ void generate(unsigned& effv, unsigned& effh) {
-        draw_cells(P, true);
-        playability(false, effv, effh);
-    }
-
-    // move (ref :330-395) after the effectiveness gate; i1/i2 are the swapped cells
-    __device__ void move(int i1, int i2, int& reward, int& is_comb, int& shuffled, unsigned& effv, unsigned& effh) {
+    // move (ref :330-378) after the effectiveness gate, up to but excluding the playability loop
+    __device__ void move_core(int i1, int i2, int& elim_out, int& is_comb) {
         n_new = 0; n_act = 0;                                // ref :343-347
         int elim = 0;
         sync();
@@ -945,23 +1002,27 @@ template <int L> struct Board {
         is_comb = comb;
         sync();  // every lane has read the swapped types before the leader starts deleting
         if (comb) {
-            if (lane == 0) combination(i1, i2);              // ref :361
+            if (lane == 0) {                                 // ref :361
+                Serial<L> q = make_serial();
+                q.combination(i1, i2);
+                take_serial(q);
+            }
             int e_cnt;
             const int e = gravity(&e_cnt);                   // ref :362-363
             elim += e_cnt;
             refill(e);                                       // ref :364
         }
+#pragma unroll 1
         for (;;) {                                           // ref :367-376
-            if (resolve_round(R - 1) == 0) break;
+            if (resolve_round() == 0) break;
             int e_cnt;
             const int e = gravity(&e_cnt);
             elim += e_cnt;
             refill(e);
         }
-        shuffled = playability(true, effv, effh);            // ref :381-391
         n_new = shfl(n_new, 0);
         n_act = shfl(n_act, 0);
-        reward = elim + n_new;                               // ref :378
+        elim_out = elim + n_new;                             // ref :378
     }
 
     __device__ bool board_is_valid() {
@@ -1026,10 +1087,10 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(cons
     if (p.init_boards) {
         b.load_board(p.init_boards, p.init_vecw);
         if (!b.board_is_valid()) b.status |= ST_INVALID_BOARD;
-        bool any;
-        b.mask_bits(effv, effh, any);
+        b.mask_bits(effv, effh);
     } else {
-        b.generate(effv, effh);
+        b.draw_cells(p.P, true);                 // generate_board (ref board.py:95-112)
+        b.playability(false, true, effv, effh);
     }
     b.store_board();
     b.store_cursors();
@@ -1044,35 +1105,28 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const
     if (gc.env >= p.N) return;
     const int env = gc.env, lane = gc.lane;
     Board<L> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
+    const long long prof_t0 = p.prof ? clock64() : 0;
     const bool want_mask = !(p.flags & FLAG_NO_MASK);
     int timer = p.timer[env];
     const int action = p.actions[env];
     unsigned effv = 0u, effh = 0u;
+    bool eff = false, have_board = false, regenerate = false;
     if (timer < 0 || timer >= p.num_moves) {
         if (p.autoreset == AUTORESET_NEXT_STEP && timer >= p.num_moves) {  // this call is the reset
-            b.load_cursors();
-            b.generate(effv, effh);
-            b.store_board();
-            b.store_cursors();
-            if (want_mask) { b.mask_to_smem(effv, effh); b.store_mask(); }
-            merge_status(b, p);
-            write_step_outputs<L>(p, env, lane, 0, 0, 0, 0, 0, 0, 0);
+            regenerate = true;
+        } else {
+            b.sync();
+            if (lane == 0) p.status[env] |= ST_NEEDS_RESET;                // ref tile_match_env.py:94-95
+            write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
             return;
         }
-        b.sync();
-        if (lane == 0) p.status[env] |= ST_NEEDS_RESET;                    // ref tile_match_env.py:94-95
-        write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
-        return;
-    }
-    if (action < 0 || action >= p.A) {                                     // ref tile_match_env.py:97
+    } else if (action < 0 || action >= p.A) {                              // ref tile_match_env.py:97
         b.sync();
         if (lane == 0) p.status[env] |= ST_BAD_ACTION;
         write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
         return;
-    }
-    // effectiveness gate (ref board.py:352): the maintained mask IS is_move_effective of the current board
-    bool eff, have_board = false;
-    if (want_mask) {
+    } else if (want_mask) {
+        // effectiveness gate (ref board.py:352): the maintained mask IS is_move_effective of the current board
         eff = p.mask[(size_t)env * p.A + action] != 0;
     } else {
         b.load_board(p.board, p.board_vecw);
@@ -1080,30 +1134,40 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const
         eff = b.effective_group(action);
     }
     b.sync();  // every lane has read timer/action/gate before any lane of the group writes state back
-    int reward = 0, is_comb = 0, shuffled = 0;
-    bool dirty = false;
-    if (eff) {
-        if (!have_board) b.load_board(p.board, p.board_vecw);
-        b.load_cursors();
-        int i1, i2;
-        b.action_cells(action, i1, i2);
-        b.move(i1, i2, reward, is_comb, shuffled, effv, effh);
-        dirty = true;
-    }
-    ++timer;                                                               // ref tile_match_env.py:100-101
-    const int terminated = timer == p.num_moves;
-    const int n_new = b.n_new, n_act = b.n_act;
+    int reward = 0, is_comb = 0, shuffled = 0, terminated = 0;
     bool zero_mask = false;
-    if (terminated) {
-        if (p.autoreset == AUTORESET_SAME_STEP) {
-            if (!dirty) b.load_cursors();
-            b.generate(effv, effh);
-            dirty = true;
-            timer = 0;
-        } else {
-            zero_mask = true;                                              // ref tile_match_env.py:119-120
+    if (!regenerate) {
+        ++timer;                                                           // ref tile_match_env.py:100-101
+        terminated = timer == p.num_moves;
+        if (terminated) {
+            if (p.autoreset == AUTORESET_SAME_STEP) { regenerate = true; timer = 0; }
+            else zero_mask = true;                                         // ref tile_match_env.py:119-120
         }
+    } else {
+        timer = 0;
     }
+    const bool dirty = eff || regenerate;
+    if (dirty) b.load_cursors();
+    // phase 0: the move itself; phase 1: generate_board of the next episode.  One call site each.
+#pragma unroll 1
+    for (int phase = 0; phase < 2; ++phase) {
+        bool clean, all_normal;
+        if (phase == 0) {
+            if (!eff) continue;
+            if (!have_board) b.load_board(p.board, p.board_vecw);
+            int i1, i2;
+            b.action_cells(action, i1, i2);
+            b.move_core(i1, i2, reward, is_comb);
+            clean = true; all_normal = false;
+        } else {
+            if (!regenerate) continue;
+            b.draw_cells(p.P, true);                                       // ref board.py:96-97
+            clean = false; all_normal = true;
+        }
+        const bool sh = b.playability(clean, all_normal, effv, effh);      // ref board.py:381-391 / :99-109
+        if (phase == 0) shuffled = sh;
+    }
+    const int n_new = b.n_new, n_act = b.n_act;
     if (dirty) { b.store_board(); b.store_cursors(); }
     if (want_mask) {
         if (zero_mask) b.store_zero_mask();
@@ -1111,6 +1175,12 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const
     }
     merge_status(b, p);
     write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled);
+    if (p.prof && lane == 0) {
+        p.prof[env * 4 + 0] = (uint32_t)(clock64() - prof_t0);
+        p.prof[env * 4 + 1] = b.prof_serial;
+        p.prof[env * 4 + 2] = b.prof_rounds;
+        p.prof[env * 4 + 3] = b.prof_iters;
+    }
 }
 
 // _get_effective_actions for every env from its current board (ref tile_match_env.py:118-124)
@@ -1123,8 +1193,7 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_mask(const
     if (terminal) { b.store_zero_mask(); return; }
     b.load_board(p.board, p.board_vecw);
     unsigned effv, effh;
-    bool any;
-    b.mask_bits(effv, effh, any);
+    b.mask_bits(effv, effh);
     b.mask_to_smem(effv, effh);
     b.store_mask();
 }
@@ -1143,17 +1212,16 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
     const int a2 = p.dbg_args ? p.dbg_args[env * 4 + 2] : 0, a3 = p.dbg_args ? p.dbg_args[env * 4 + 3] : 0;
     int result = 0;
     const int C = p.C;
+    b.sync();
     switch (p.dbg_op) {
         case OP_GRAVITY: b.gravity(&result); break;
         case OP_REFILL: {
-            int e = 0;  // refill() expects the post-gravity layout; a general board is handled row by row instead
-            b.sync();
+            // refill() expects the post-gravity layout; a general board is handled row by row instead:
             // count empties row-major and assign draws in that order (ref :231-241)
             int total = 0;
             for (int r = 0; r < p.R; ++r) {
                 const bool em = lane < C && b.col[r * C + lane] == 0 && b.typ[r * C + lane] == 0;
-                const unsigned m = b.ballot(em);
-                total += __popc(m);
+                total += __popc(b.ballot(em));
             }
             for (int ps = 0; ps < total; ps += Cfg<L>::NW) {
                 const int nw = min(Cfg<L>::NW, total - ps);
@@ -1165,7 +1233,8 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
                     if (em) {
                         const int rank = base + __popc(m & b.lt_mask());
                         if (rank >= ps && rank < ps + nw) {
-                            b.col[r * C + lane] = (int8_t)b.draw_colour(rank, rank - ps);
+                            b.col[r * C + lane] = (int8_t)(p.use_inj ? b.injected_colour(rank)
+                                                                     : 1 + (int)__umulhi(b.s.wbuf[rank - ps], (uint32_t)p.K));
                             b.typ[r * C + lane] = 1;
                         }
                     }
@@ -1174,16 +1243,23 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
                 b.sync();
             }
             b.dcur += (uint64_t)total;
-            (void)e;
             result = total;
             break;
         }
-        case OP_RESOLVE_ROUND: result = b.resolve_round(p.R - 1); break;
+        case OP_RESOLVE_ROUND: result = b.resolve_round(); break;
         case OP_ACTIVATE:
-            if (lane == 0) { b.nzc = -1; b.activate(a0 * C + a1, a2, a3 == 0); }
+            if (lane == 0) {
+                Serial<L> q = b.make_serial();
+                q.activate(a0 * C + a1, a2, a3 == 0);
+                b.take_serial(q);
+            }
             break;
         case OP_COMBINE:
-            if (lane == 0) b.combination(a0 * C + a1, a2 * C + a3);
+            if (lane == 0) {
+                Serial<L> q = b.make_serial();
+                q.combination(a0 * C + a1, a2 * C + a3);
+                b.take_serial(q);
+            }
             break;
         case OP_MOVE: {
             int reward = 0, is_comb = 0, shuffled = 0;
@@ -1191,24 +1267,26 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
             const int i1 = a0 * C + a1, i2 = a2 * C + a3;
             b.n_new = 0; b.n_act = 0;
             bool eff = false;
-            if (lane == 0) eff = b.effective_literal(i1, i2);
+            if (lane == 0) eff = effective_literal(b.col, b.typ, p.R, C, i1, i2);
             eff = b.shfl((int)eff, 0) != 0;
-            if (eff) b.move(i1, i2, reward, is_comb, shuffled, effv, effh);
+            if (eff) {
+                b.move_core(i1, i2, reward, is_comb);
+                shuffled = b.playability(true, false, effv, effh);
+            }
             if (lane == 0) { p.is_comb[env] = (uint8_t)is_comb; p.shuffled[env] = (uint8_t)shuffled; }
             result = reward;
             break;
         }
         case OP_EFFECTIVE: {
             bool eff = false;
-            if (lane == 0) eff = b.effective_literal(a0 * C + a1, a2 * C + a3);
+            if (lane == 0) eff = effective_literal(b.col, b.typ, p.R, C, a0 * C + a1, a2 * C + a3);
             result = b.shfl((int)eff, 0);
             break;
         }
-        case OP_GENERATE: { unsigned v, h; b.generate(v, h); break; }
+        case OP_GENERATE: { unsigned v, h; b.draw_cells(p.P, true); b.playability(false, true, v, h); break; }
         case OP_SHUFFLE: b.shuffle(); break;
         case OP_COUNT_LINES: {
-            b.sync();
-            const typename Board<L>::Scan sc = b.scan_lines(p.R - 1);
+            const typename Board<L>::Scan sc = b.scan_lines(p.R - 1, false);
             result = sc.rstar < 0 ? 0 : b.build_line_table(sc);
             break;
         }
@@ -1218,12 +1296,12 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
     b.n_act = b.shfl(b.n_act, 0);
     b.store_board();
     b.store_cursors();
+    merge_status(b, p);
     if (lane == 0) {
         p.reward[env] = result;
         p.new_specials[env] = b.n_new;
         p.activated[env] = b.n_act;
     }
-    merge_status(b, p);
 }
 
 // OneHotWrapper._one_hot_encode_board (ref wrappers.py:54-69).  One thread per 4 output bytes (or 1 float4).
