@@ -108,8 +108,18 @@ static void run_group(int L, int first_tid, void (*fn)()) {
 using namespace tmg;
 
 static Params g_params;
-template <int L> static void e_reset() { k_reset<L>(g_params); }
-template <int L> static void e_step() { k_step<L>(g_params); }
+template <int L> static void e_reset() {
+    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_reset<16, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_reset<16, 9, 9>(g_params);
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_reset<32, 32, 32>(g_params);
+    else k_reset<L, 0, 0>(g_params);
+}
+template <int L> static void e_step() {
+    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_step<16, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_step<16, 9, 9>(g_params);
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_step<32, 32, 32>(g_params);
+    else k_step<L, 0, 0>(g_params);
+}
 template <int L> static void e_mask() { k_mask<L>(g_params); }
 template <int L> static void e_debug() { k_debug<L>(g_params); }
 

@@ -42,6 +42,19 @@ int check_device(int device) {
     return TMG_OK;
 }
 
+// (lanes per board, compile-time rows, compile-time cols); RT = CT = 0 is the runtime-shape kernel
+template <int L_, int R_, int C_> struct Shape { static constexpr int L = L_, R = R_, C = C_; };
+template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
+    const int R = e->p.R, C = e->p.C;
+    if (R == 10 && C == 10) return f(Shape<16, 10, 10>());
+    if (R == 9 && C == 9) return f(Shape<16, 9, 9>());
+    if (R == 32 && C == 32) return f(Shape<32, 32, 32>());
+    switch (e->L) {
+        case 8: return f(Shape<8, 0, 0>());
+        case 16: return f(Shape<16, 0, 0>());
+        default: return f(Shape<32, 0, 0>());
+    }
+}
 template <typename F> int launch_by_lanes(const tmg_env* e, F&& f) {
     switch (e->L) {
         case 8: return f(std::integral_constant<int, 8>());
@@ -204,9 +217,10 @@ int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boar
     p.init_boards = init_boards_dev;
     p.init_vecw = init_boards_dev ? ptr_vec_width(init_boards_dev, p.board_vecw) : p.board_vecw;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return launch_by_lanes(e, [&](auto lanes) {
-        constexpr int L = decltype(lanes)::value;
-        k_reset<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+    return launch_by_shape(e, [&](auto shape) {
+        typedef decltype(shape) S;
+        constexpr int L = S::L;
+        k_reset<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
 }
@@ -217,9 +231,10 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
     Params p = e->p;
     p.actions = actions_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return launch_by_lanes(e, [&](auto lanes) {
-        constexpr int L = decltype(lanes)::value;
-        k_step<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+    return launch_by_shape(e, [&](auto shape) {
+        typedef decltype(shape) S;
+        constexpr int L = S::L;
+        k_step<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
 }

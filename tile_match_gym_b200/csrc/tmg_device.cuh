@@ -217,302 +217,10 @@ __device__ __noinline__ void shuffle_serial(int8_t* col, int8_t* typ, int P, uin
 }
 
 // ======================================================================================================
-// Serial context: the order-dependent list semantics of the reference, run by the group's leader lane over
-// the shared-memory tables.  Kept out of line so the hot parallel code stays small.
-// ======================================================================================================
-template <int L> struct Serial {
-    typedef Cfg<L> CF;
-    GroupSmem<L>& s;
-    int8_t* col;
-    int8_t* typ;
-    int R, C, P;
-    uint32_t specials;
-    uint32_t status;
-    int n_new, n_act;  // ref :343-344
-    int nzc;           // number of cells with colour != 0; -1 = not counted yet
-
-    __device__ __forceinline__ void del_cell(int i) {
-        if (nzc >= 0 && col[i] != 0) --nzc;
-        col[i] = 0;
-        typ[i] = 0;
-    }
-    __device__ void count_nzc() {
-        int n = 0;
-        for (int i = 0; i < P; ++i) n += (col[i] != 0);
-        nzc = n;
-    }
-    // frame: kind(2) | cell(10) << 2 | cursor(11) << 12 | colour(5) << 23
-    __device__ __forceinline__ static uint32_t frame(int kind, int cell, int cursor, int mc) {
-        return (uint32_t)kind | ((uint32_t)cell << 2) | ((uint32_t)cursor << 12) | ((uint32_t)mc << 23);
-    }
-    // entry of activate_special (ref :473-499 + the set-up of the cookie branch :530-544); pushes a frame
-    __device__ void enter_activation(int cell, int t, bool counted, int& sp) {
-        if (nzc < 0) count_nzc();
-        if (nzc == 0) return;                      // ref :488-489
-        if (t == 0 || t == 1) { status |= ST_INTERNAL; return; }  // ref :491-492 raises
-        del_cell(cell);                            // ref :496
-        if (counted) ++n_act;                      // ref :498-499
-        int kind, mc = 0;
-        if (t == 2) kind = 0;
-        else if (t == 3) kind = 1;
-        else if (t == 4) kind = 2;
-        else if (t == -1) {
-            kind = 3;
-            if (nzc == 0) return;                  // ref :532-534
-            for (int k = 0; k < 32; ++k) s.cnt[k] = 0;
-            for (int i = 0; i < P; ++i) { const int x = col[i]; if (x > 0 && x < 32) ++s.cnt[x]; }
-            int best = 0;
-            for (int k = 1; k < 32; ++k) if (s.cnt[k] > best) { best = s.cnt[k]; mc = k; }  // ref :536-537
-            for (int i = 0; i < P; ++i) if (col[i] == mc && typ[i] == 1) del_cell(i);       // ref :540-544
-        } else { status |= ST_INTERNAL; return; }  // ref :555-556 raises
-        if (sp >= CF::DFS) { status |= ST_DFS_OVERFLOW; return; }
-        s.stack[sp++] = frame(kind, cell, 0, mc);
-    }
-    // activate_special (ref :473-556) as an explicit-stack DFS that re-reads live cells in the reference's order
-    __device__ __noinline__ void activate(int cell0, int t0, bool counted) {
-        int sp = 0;
-        enter_activation(cell0, t0, counted, sp);
-        while (sp > 0) {
-            const uint32_t f = s.stack[sp - 1];
-            const int kind = (int)(f & 3u), cell = (int)((f >> 2) & 1023u), mc = (int)(f >> 23);
-            int cur = (int)((f >> 12) & 2047u);
-            const int r0 = cell / C, c0 = cell - r0 * C;
-            int target = -1;
-            if (kind == 0) {                        // vertical laser: rows top to bottom (ref :502-507)
-                if (cur < R) target = cur * C + c0;
-                ++cur;
-            } else if (kind == 1) {                 // horizontal laser: columns left to right (ref :510-515)
-                if (cur < C) target = r0 * C + cur;
-                ++cur;
-            } else if (kind == 2) {                 // bomb: clipped 3x3, row-major (ref :517-528)
-                const int min_r = max(r0 - 1, 0), max_r = min(r0 + 1, R - 1);
-                const int min_c = max(c0 - 1, 0), max_c = min(c0 + 1, C - 1);
-                const int w = max_c - min_c + 1;
-                if (cur < w * (max_r - min_r + 1)) target = (min_r + cur / w) * C + min_c + cur % w;
-                ++cur;
-            } else {                                // cookie: specials of the chosen colour, row-major (ref :547-554)
-                while (cur < P && !(col[cur] == mc && typ[cur] > 1)) ++cur;
-                if (cur < P) target = cur;
-                ++cur;
-            }
-            if (target < 0) { --sp; continue; }
-            s.stack[sp - 1] = frame(kind, cell, cur, mc);
-            const int t = typ[target];
-            if (not01(t)) enter_activation(target, t, true, sp);  // nested calls always count (ref :505,513,526,554)
-            else if (kind != 3) del_cell(target);
-        }
-    }
-
-    // get_special_creation_pos (ref :429-458) on s.match[0..n)
-    __device__ __noinline__ int creation_pos(int n, int ntaken, bool straight) {
-        auto is_taken = [&](int cell) {
-            for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
-            return false;
-        };
-        int nv = 0;
-        for (int k = 0; k < n; ++k) nv += !is_taken(s.match[k]);
-        if (nv == 0) { status |= ST_INTERNAL; return -1; }  // reference: IndexError
-        if (!straight) {                                    // ref :441-450
-            int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
-            for (int k = 0; k < n; ++k) {                   // max(xs, key=xs.count): first element with the top count
-                const int rr = s.match[k] / C, cc = s.match[k] % C;
-                int nr = 0, nc = 0;
-                for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
-                if (nr > best_rc) { best_rc = nr; best_r = rr; }
-                if (nc > best_cc) { best_cc = nc; best_c = cc; }
-            }
-            const int corner = best_r * C + best_c;
-            int best = -1, bestd = 0;
-            for (int k = 0; k < n; ++k) {
-                const int cell = s.match[k];
-                if (is_taken(cell)) continue;
-                if (cell == corner) return corner;          // ref :446-447
-                const int dr = cell / C - best_r, dc = cell % C - best_c, d = dr * dr + dc * dc;
-                if (best < 0 || d < bestd) { best = cell; bestd = d; }  // stable: first minimum (ref :449)
-            }
-            return best;
-        }
-        // straight: the match is already sorted by (row, col); pick the middle of the valid cells (ref :453-458)
-        const int want = (nv % 2 == 0) ? nv / 2 - 1 : nv / 2;
-        int seen = 0;
-        for (int k = 0; k < n; ++k) {
-            if (is_taken(s.match[k])) continue;
-            if (seen == want) return s.match[k];
-            ++seen;
-        }
-        return -1;
-    }
-
-    // process_colour_lines (ref :269-327) fused with resolve_colour_matches (ref :397-427): the creation cell
-    // of a match depends only on coordinates, so each match is resolved as soon as it is classified; the new
-    // specials are written after all deletions, as in the reference.
-    __device__ __noinline__ void process_and_resolve(int n) {
-        nzc = -1;
-        // ref :282: stable sort by the first cell's row == sort by key (keys are unique)
-        for (int i = 0; i < n; ++i) s.order[i] = (uint8_t)i;
-        for (int i = 1; i < n; ++i) {
-            const uint8_t v = s.order[i];
-            const uint32_t kv = s.line_key[v];
-            int j = i - 1;
-            while (j >= 0 && s.line_key[s.order[j]] > kv) { s.order[j + 1] = s.order[j]; --j; }
-            s.order[j + 1] = v;
-        }
-        int qh = 0, qn = n, nslots = n, ncq = 0, ntaken = 0;
-        const bool sp_cookie = specials & SP_COOKIE, sp_v = specials & SP_VLASER, sp_h = specials & SP_HLASER,
-                   sp_bomb = specials & SP_BOMB;
-        while (qh < qn) {
-            const int li = s.order[qh++];                    // ref :285 pop(0)
-            const int len = s.line_len[li];
-            const uint16_t* cells = s.line_cells[li];
-            int mlen = 0, name = NAME_NORMAL, colour = s.line_colour[li];
-            bool have = false;
-            if (len >= 5 && sp_cookie) {                     // ref :287-292
-                for (int k = 0; k < 5; ++k) s.match[mlen++] = cells[k];
-                name = NAME_COOKIE; colour = 0; have = true;
-                if (len - 5 > 2) {
-                    if (nslots < CF::ML && qn < CF::ML) {
-                        const int ns = nslots++;
-                        for (int k = 5; k < len; ++k) s.line_cells[ns][k - 5] = cells[k];
-                        s.line_len[ns] = (uint8_t)(len - 5);
-                        s.line_colour[ns] = s.line_colour[li];
-                        s.order[qn++] = (uint8_t)ns;
-                    } else status |= ST_LINE_OVERFLOW;
-                }
-            } else if (len == 4) {                           // ref :294-302
-                for (int k = 0; k < 4; ++k) s.match[mlen++] = cells[k];
-                const bool horizontal = (cells[0] / C) == (cells[1] / C);
-                name = (horizontal && sp_h) ? NAME_HLASER : (sp_v ? NAME_VLASER : NAME_NORMAL);
-                have = true;
-            } else {
-                int hit = -1, shared = -1;
-                if (sp_bomb) {                               // ref :304-308: first queued line sharing a cell
-                    for (int q = qh; q < qn && hit < 0; ++q) {
-                        const int lj = s.order[q];
-                        for (int k = 0; k < len && hit < 0; ++k)
-                            for (int u = 0; u < s.line_len[lj]; ++u)
-                                if (s.line_cells[lj][u] == cells[k]) { hit = q; shared = cells[k]; break; }
-                    }
-                }
-                if (hit >= 0) {                              // ref :309-320
-                    const int lj = s.order[hit];
-                    const int llen = s.line_len[lj];
-                    uint16_t* lc = s.line_cells[lj];
-                    const int sr = shared / C, scc = shared % C;
-                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
-                    // first three of the stable sort of l by Manhattan distance (ref :310)
-                    int picked[3] = {-1, -1, -1};
-                    const int take = llen < 3 ? llen : 3;
-                    for (int a = 0; a < take; ++a) {
-                        int bi = -1, bd = 0;
-                        for (int u = 0; u < llen; ++u) {
-                            if (u == picked[0] || u == picked[1]) continue;
-                            const int d = abs(lc[u] / C - sr) + abs(lc[u] % C - scc);
-                            if (bi < 0 || d < bd) { bi = u; bd = d; }
-                        }
-                        picked[a] = bi;
-                        bool in_line = false;
-                        for (int k = 0; k < len; ++k) in_line |= (cells[k] == lc[bi]);
-                        if (!in_line) s.match[mlen++] = lc[bi];  // ref :312
-                    }
-                    name = NAME_BOMB; have = true;
-                    if (llen < 6) {                          // ref :315-316 (lines are distinct by value, see DESIGN.md)
-                        for (int q = hit; q + 1 < qn; ++q) s.order[q] = s.order[q + 1];
-                        --qn;
-                    } else {                                 // ref :317-319: drop the three cells, keep the order
-                        int w = 0;
-                        for (int u = 0; u < llen; ++u)
-                            if (u != picked[0] && u != picked[1] && u != picked[2]) lc[w++] = lc[u];
-                        s.line_len[lj] = (uint8_t)w;
-                    }
-                } else if (len >= 3) {                       // ref :322-325
-                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
-                    have = true;
-                }
-            }
-            if (!have) continue;
-            if (name != NAME_NORMAL) {                       // ref :414-418
-                const int pos = creation_pos(mlen, ntaken, name != NAME_BOMB);
-                if (pos >= 0 && ntaken < CF::ML) s.taken[ntaken++] = (uint16_t)pos;
-                if (ncq < CF::ML) {
-                    s.cq_pos[ncq] = (uint16_t)(pos < 0 ? 0xffff : pos);
-                    s.cq_type[ncq] = (int8_t)name;
-                    s.cq_colour[ncq] = (uint8_t)colour;
-                    ++ncq;
-                }
-            }
-            for (int k = 0; k < mlen; ++k) {                 // ref :460-471
-                const int cell = s.match[k];
-                const int t = typ[cell];
-                if (not01(t)) activate(cell, t, true);
-                else del_cell(cell);
-            }
-        }
-        for (int i = 0; i < ncq; ++i) {                      // ref :426-427 -> create_special :572-597
-            ++n_new;
-            if (s.cq_pos[i] == 0xffff) continue;
-            col[s.cq_pos[i]] = (int8_t)s.cq_colour[i];
-            typ[s.cq_pos[i]] = s.cq_type[i];
-        }
-    }
-
-    // combination_match (ref :600-719)
-    __device__ __noinline__ void combination(int i1, int i2) {
-        n_act += 2;                                          // ref :609
-        nzc = -1;
-        const int t1 = typ[i1], k1 = col[i1], t2 = typ[i2], k2 = col[i2];
-        const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
-        if (t1 == -1 && t2 == -1) {                          // ref :615-616
-            for (int i = 0; i < P; ++i) { col[i] = 0; typ[i] = 0; }
-        } else if ((t1 == -1 && t2 == 1) || (t1 == 1 && t2 == -1)) {  // ref :619-641
-            const int ck = (t1 == -1) ? i1 : i2;
-            const int kk = (t1 == -1) ? k2 : k1;
-            del_cell(ck);                                    // ref :626,628
-            for (int i = 0; i < P; ++i) if (col[i] == kk && typ[i] == 1) del_cell(i);   // ref :631-635
-            // snapshot mask colour==kk & type>1, visited row-major; cells can only disappear meanwhile (ref :638-640)
-            for (int i = 0; i < P; ++i)
-                if (col[i] == kk && typ[i] > 1) activate(i, typ[i], false);
-            n_act -= 1;                                      // ref :641
-        } else if ((t1 == -1 && t2 >= 2) || (t1 >= 2 && t2 == -1)) {  // ref :644-660
-            const int ck = (t1 == -1) ? i1 : i2;
-            const int kk = (t1 == -1) ? k2 : k1;
-            const int tt = (t1 == -1) ? t2 : t1;
-            del_cell(ck);                                    // ref :651
-            // ref :654 snapshot of colour==kk; a cell leaves the snapshot only by deletion (colour -> 0), and a cell
-            // that was not in it never gains the colour, so a live test of colour==kk is the same set.
-            for (int i = 0; i < P; ++i) if (col[i] == kk && typ[i] == 1) typ[i] = (int8_t)tt;  // ref :655-657
-            for (int i = 0; i < P; ++i)
-                if (col[i] == kk && not01(typ[i])) activate(i, typ[i], false);                 // ref :660
-        } else if ((t1 == 2 || t1 == 3) && (t2 == 2 || t2 == 3)) {    // ref :663-674
-            del_cell(i1); del_cell(i2);
-            const int cell = min(r1, r2) * C + min(c1, c2);
-            activate(cell, 2, false);
-            activate(cell, 3, false);
-        } else if ((t1 == 4 && (t2 == 2 || t2 == 3)) || (t2 == 4 && (t1 == 2 || t1 == 3))) {  // ref :677-696
-            del_cell(i1); del_cell(i2);
-            const int r = min(r1, r2), c = min(c1, c2);
-            const int min_r = max(r - 1, 0), max_r = min(r + 1, R - 1);
-            const int min_c = max(c - 1, 0), max_c = min(c + 1, C - 1);
-            for (int i = min_r; i <= max_r; ++i) activate(i * C + c, 3, false);
-            for (int j = min_c; j <= max_c; ++j) activate(r * C + j, 2, false);
-        } else if (t1 == 4 && t2 == 4) {                     // ref :699-719
-            del_cell(i1); del_cell(i2);
-            const int r = min(r1, r2), c = min(c1, c2);
-            const int min_r = max(r - 2, 0), max_r = min(r + 2, R - 1);
-            const int min_c = max(c - 2, 0), max_c = min(c + 2, C - 1);
-            for (int i = min_r; i <= max_r; ++i)
-                for (int j = min_c; j <= max_c; ++j) {
-                    const int q = i * C + j;
-                    if (typ[q] == 1) del_cell(q);
-                    else if (typ[q] != 0) activate(q, typ[q], false);
-                }
-        }
-    }
-};
-
-// ======================================================================================================
 // One board owned by a group of L lanes
 // ======================================================================================================
-template <int L> struct Board {
+// RT/CT > 0 fix the board shape at compile time (full unrolling, immediate shared-memory offsets); 0 = runtime shape.
+template <int L, int RT = 0, int CT = 0> struct Board {
     typedef Cfg<L> CF;
     GroupSmem<L>& s;
     const Params& p;
@@ -530,9 +238,9 @@ template <int L> struct Board {
     uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
 
     __device__ Board(GroupSmem<L>& sm, const Params& pp, int lane_, unsigned gmask_, int gshift_, int env_)
-        : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(pp.R), C(pp.C), P(pp.P), K(pp.K),
-          col(sm.board), typ(sm.board + pp.P), dcur(0), scur(0), gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)),
-          status(0), n_new(0), n_act(0) {}
+        : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(RT ? RT : pp.R), C(CT ? CT : pp.C),
+          P(RT ? RT * CT : pp.P), K(pp.K), col(sm.board), typ(sm.board + (RT ? RT * CT : pp.P)), dcur(0), scur(0),
+          gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)), status(0), n_new(0), n_act(0) {}
 
     // ---- group collectives ---------------------------------------------------------------------------
     __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
@@ -687,8 +395,8 @@ template <int L> struct Board {
         if (lane < C) {
             int prev = -3;
             const bool has_right = lane + 1 < C;
-#pragma unroll 4
-            for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int r = 0; r < (RT ? RT : R); ++r) {
                 const int i = r * C + lane;
                 const int x = col[i];
                 const int xr = has_right ? (int)col[i + 1] : -2;
@@ -816,12 +524,311 @@ template <int L> struct Board {
         return n;
     }
 
-    // ---- leader-lane serial sections ---------------------------------------------------------------------
-    __device__ __forceinline__ Serial<L> make_serial() {
-        Serial<L> q{s, col, typ, R, C, P, p.specials, 0u, n_new, n_act, -1};
-        return q;
+    // =====================================================================================================
+    // Order-dependent part of a cascade round.  Classification of the lines (pure coordinate work on small
+    // tables) runs on the leader lane; everything that touches the board -- deleting match cells, the special
+    // activation DFS, combination matches -- runs on ALL lanes with uniform control flow, so that every sweep
+    // (laser column/row, bomb window, cookie scans, colour histogram) is one parallel step.  The reference's
+    // visit order is kept exactly: a sweep deletes the normal tiles up to the first special in its order in
+    // one go (no activation can happen in between), then enters that special, then continues after it.
+    // =====================================================================================================
+    __device__ __forceinline__ uint16_t* mlist() { return reinterpret_cast<uint16_t*>(s.mask); }  // mask staging is free now
+    static constexpr int MCAP = CF::MAXP;
+
+    // number of cells whose colour is not 0 (ref :488 np.all(board[0] == 0), :532-533)
+    __device__ __forceinline__ int count_nonzero_colours() {
+        int n = 0;
+        if (lane < C) {
+#pragma unroll
+            for (int r = 0; r < (RT ? RT : R); ++r) n += (col[r * C + lane] != 0);
+        }
+        return radd(n);
     }
-    __device__ __forceinline__ void take_serial(const Serial<L>& q) { status |= q.status; n_new = q.n_new; n_act = q.n_act; }
+    // frame: kind(2) | cell(10) << 2 | cursor(11) << 12 | colour(5) << 23
+    __device__ __forceinline__ static uint32_t frame(int kind, int cell, int cursor, int mc) {
+        return (uint32_t)kind | ((uint32_t)cell << 2) | ((uint32_t)cursor << 12) | ((uint32_t)mc << 23);
+    }
+    // entry of activate_special (ref :473-499 + the set-up of the cookie branch :530-544); pushes a frame.
+    // All lanes, uniform arguments.  Board writes of other lanes must be visible (callers sync before).
+    __device__ void enter_activation(int cell, int t, bool counted, int& sp) {
+        int nz = count_nonzero_colours();
+        if (nz == 0) return;                                   // ref :488-489
+        if (t == 0 || t == 1) { status |= ST_INTERNAL; return; }  // ref :491-492 raises
+        const int own_nz = col[cell] != 0;
+        sync();                                                // every lane has read the cell
+        if (lane == 0) { col[cell] = 0; typ[cell] = 0; }       // ref :496
+        if (counted) ++n_act;                                  // ref :498-499
+        int kind, mc = 0;
+        if (t == 2) kind = 0;
+        else if (t == 3) kind = 1;
+        else if (t == 4) kind = 2;
+        else if (t == -1) {
+            kind = 3;
+            nz -= own_nz;
+            if (nz == 0) { sync(); return; }                   // ref :532-534
+            sync();
+            int best = 0;                                      // ref :536-537: most common colour, lowest on ties
+            for (int k = 1; k < 32; ++k) {
+                if (k > K && best > 0 && k > 8) break;         // colours above K only exist on hand-made boards
+                int c = 0;
+                if (lane < C) {
+#pragma unroll
+                    for (int r = 0; r < (RT ? RT : R); ++r) c += (col[r * C + lane] == k);
+                }
+                c = radd(c);
+                if (c > best) { best = c; mc = k; }
+            }
+            if (lane < C) {                                    // ref :540-544: delete its normal tiles
+#pragma unroll
+                for (int r = 0; r < (RT ? RT : R); ++r) {
+                    const int i = r * C + lane;
+                    if (col[i] == mc && typ[i] == 1) { col[i] = 0; typ[i] = 0; }
+                }
+            }
+        } else { status |= ST_INTERNAL; sync(); return; }      // ref :555-556 raises
+        if (sp >= CF::DFS) { status |= ST_DFS_OVERFLOW; sync(); return; }
+        if (lane == 0) s.stack[sp] = frame(kind, cell, 0, mc);
+        ++sp;
+        sync();
+    }
+    // first index i in [cur, n) (lanes test i = base + lane) for which pred(i) holds, else n
+    template <typename F> __device__ __forceinline__ int first_in_order(int cur, int n, F&& pred) {
+        for (int base = cur; base < n; base += L) {
+            const int i = base + lane;
+            const unsigned m = ballot(i < n && pred(i));
+            if (m) return base + __ffs((int)m) - 1;
+        }
+        return n;
+    }
+    template <typename F> __device__ __forceinline__ void delete_in_order(int cur, int end, F&& cell_of) {
+        for (int i = cur + lane; i < end; i += L) {
+            const int q = cell_of(i);
+            col[q] = 0;
+            typ[q] = 0;
+        }
+    }
+    // activate_special (ref :473-556) as an explicit-stack DFS; all lanes, uniform control flow
+    __device__ void activate(int cell0, int t0, bool counted) {
+        int sp = 0;
+        enter_activation(cell0, t0, counted, sp);
+        while (sp > 0) {
+            sync();
+            const uint32_t f = s.stack[sp - 1];
+            const int kind = (int)(f & 3u), cell = (int)((f >> 2) & 1023u), mc = (int)(f >> 23);
+            const int cur = (int)((f >> 12) & 2047u);
+            const int r0 = cell / C, c0 = cell - r0 * C;
+            int target = -1, next = 0;
+            if (kind == 0) {                                   // vertical laser: rows top to bottom (ref :502-507)
+                auto cell_of = [&](int i) { return i * C + c0; };
+                const int first = first_in_order(cur, R, [&](int i) { return not01(typ[cell_of(i)]); });
+                delete_in_order(cur, first, cell_of);
+                if (first < R) { target = cell_of(first); next = first + 1; }
+            } else if (kind == 1) {                            // horizontal laser: columns left to right (ref :510-515)
+                auto cell_of = [&](int i) { return r0 * C + i; };
+                const int first = first_in_order(cur, C, [&](int i) { return not01(typ[cell_of(i)]); });
+                delete_in_order(cur, first, cell_of);
+                if (first < C) { target = cell_of(first); next = first + 1; }
+            } else if (kind == 2) {                            // bomb: clipped 3x3, row-major (ref :517-528)
+                const int min_r = max(r0 - 1, 0), max_r = min(r0 + 1, R - 1);
+                const int min_c = max(c0 - 1, 0), max_c = min(c0 + 1, C - 1);
+                const int w = max_c - min_c + 1, n = w * (max_r - min_r + 1);
+                auto cell_of = [&](int i) { return (min_r + i / w) * C + min_c + i % w; };
+                const int first = first_in_order(cur, n, [&](int i) { return not01(typ[cell_of(i)]); });
+                delete_in_order(cur, first, cell_of);
+                if (first < n) { target = cell_of(first); next = first + 1; }
+            } else {                                           // cookie: specials of its colour, row-major (ref :547-554)
+                int cand = 1 << 20;
+                if (lane < C)
+                    for (int r = cur / C; r < R; ++r) {
+                        const int i = r * C + lane;
+                        if (i >= cur && col[i] == mc && typ[i] > 1) { cand = i; break; }
+                    }
+                cand = rmin(cand);
+                if (cand < (1 << 20)) { target = cand; next = cand + 1; }
+            }
+            if (target < 0) { --sp; continue; }
+            const int t = typ[target];
+            sync();                                            // deletions of this sweep are visible; frame can be updated
+            if (lane == 0) s.stack[sp - 1] = frame(kind, cell, next, mc);
+            enter_activation(target, t, true, sp);             // nested calls always count (ref :505,513,526,554)
+        }
+        sync();
+    }
+
+    // get_special_creation_pos (ref :429-458) on s.match[0..n); leader lane
+    __device__ __forceinline__ int creation_pos(int n, int ntaken, bool straight) {
+        auto is_taken = [&](int cell) {
+            for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
+            return false;
+        };
+        int nv = 0;
+        for (int k = 0; k < n; ++k) nv += !is_taken(s.match[k]);
+        if (nv == 0) return -1;                                 // reference: IndexError
+        if (!straight) {                                        // ref :441-450
+            int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
+            for (int k = 0; k < n; ++k) {                       // max(xs, key=xs.count): first element with the top count
+                const int rr = s.match[k] / C, cc = s.match[k] % C;
+                int nr = 0, nc = 0;
+                for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
+                if (nr > best_rc) { best_rc = nr; best_r = rr; }
+                if (nc > best_cc) { best_cc = nc; best_c = cc; }
+            }
+            const int corner = best_r * C + best_c;
+            int best = -1, bestd = 0;
+            for (int k = 0; k < n; ++k) {
+                const int cell = s.match[k];
+                if (is_taken(cell)) continue;
+                if (cell == corner) return corner;              // ref :446-447
+                const int dr = cell / C - best_r, dc = cell % C - best_c, d = dr * dr + dc * dc;
+                if (best < 0 || d < bestd) { best = cell; bestd = d; }  // stable: first minimum (ref :449)
+            }
+            return best;
+        }
+        // straight: the match is already sorted by (row, col); pick the middle of the valid cells (ref :453-458)
+        const int want = (nv % 2 == 0) ? nv / 2 - 1 : nv / 2;
+        int seen = 0;
+        for (int k = 0; k < n; ++k) {
+            if (is_taken(s.match[k])) continue;
+            if (seen == want) return s.match[k];
+            ++seen;
+        }
+        return -1;
+    }
+
+    // process_colour_lines (ref :269-327) + the creation cells of resolve_colour_matches (ref :414-418); leader lane.
+    // Writes the cells of all matches, in resolve order, to mlist() and the creation queue to s.cq_*.
+    // Returns nm | ncq << 16 | flags << 24 (flag 1: table overflow, flag 2: no valid creation cell).
+    __device__ __forceinline__ uint32_t classify_lines(int n) {
+        // ref :282: stable sort by the first cell's row == sort by key (keys are unique)
+        for (int i = 0; i < n; ++i) s.order[i] = (uint8_t)i;
+        for (int i = 1; i < n; ++i) {
+            const uint8_t v = s.order[i];
+            const uint32_t kv = s.line_key[v];
+            int j = i - 1;
+            while (j >= 0 && s.line_key[s.order[j]] > kv) { s.order[j + 1] = s.order[j]; --j; }
+            s.order[j + 1] = v;
+        }
+        uint16_t* out = mlist();
+        int qh = 0, qn = n, nslots = n, ncq = 0, ntaken = 0, nm = 0;
+        uint32_t flags = 0u;
+        const bool sp_cookie = p.specials & SP_COOKIE, sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER,
+                   sp_bomb = p.specials & SP_BOMB;
+        while (qh < qn) {
+            const int li = s.order[qh++];                    // ref :285 pop(0)
+            const int len = s.line_len[li];
+            const uint16_t* cells = s.line_cells[li];
+            int mlen = 0, name = NAME_NORMAL, colour = s.line_colour[li];
+            bool have = false;
+            if (len >= 5 && sp_cookie) {                     // ref :287-292
+                for (int k = 0; k < 5; ++k) s.match[mlen++] = cells[k];
+                name = NAME_COOKIE; colour = 0; have = true;
+                if (len - 5 > 2) {
+                    if (nslots < CF::ML && qn < CF::ML) {
+                        const int ns = nslots++;
+                        for (int k = 5; k < len; ++k) s.line_cells[ns][k - 5] = cells[k];
+                        s.line_len[ns] = (uint8_t)(len - 5);
+                        s.line_colour[ns] = s.line_colour[li];
+                        s.order[qn++] = (uint8_t)ns;
+                    } else flags |= 1u;
+                }
+            } else if (len == 4) {                           // ref :294-302
+                for (int k = 0; k < 4; ++k) s.match[mlen++] = cells[k];
+                const bool horizontal = (cells[0] / C) == (cells[1] / C);
+                name = (horizontal && sp_h) ? NAME_HLASER : (sp_v ? NAME_VLASER : NAME_NORMAL);
+                have = true;
+            } else {
+                int hit = -1, shared = -1;
+                if (sp_bomb) {                               // ref :304-308: first queued line sharing a cell
+                    for (int q = qh; q < qn && hit < 0; ++q) {
+                        const int lj = s.order[q];
+                        for (int k = 0; k < len && hit < 0; ++k)
+                            for (int u = 0; u < s.line_len[lj]; ++u)
+                                if (s.line_cells[lj][u] == cells[k]) { hit = q; shared = cells[k]; break; }
+                    }
+                }
+                if (hit >= 0) {                              // ref :309-320
+                    const int lj = s.order[hit];
+                    const int llen = s.line_len[lj];
+                    uint16_t* lc = s.line_cells[lj];
+                    const int sr = shared / C, scc = shared % C;
+                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
+                    // first three of the stable sort of l by Manhattan distance (ref :310)
+                    int picked[3] = {-1, -1, -1};
+                    const int take = llen < 3 ? llen : 3;
+                    for (int a = 0; a < take; ++a) {
+                        int bi = -1, bd = 0;
+                        for (int u = 0; u < llen; ++u) {
+                            if (u == picked[0] || u == picked[1]) continue;
+                            const int d = abs(lc[u] / C - sr) + abs(lc[u] % C - scc);
+                            if (bi < 0 || d < bd) { bi = u; bd = d; }
+                        }
+                        picked[a] = bi;
+                        bool in_line = false;
+                        for (int k = 0; k < len; ++k) in_line |= (cells[k] == lc[bi]);
+                        if (!in_line) s.match[mlen++] = lc[bi];  // ref :312
+                    }
+                    name = NAME_BOMB; have = true;
+                    if (llen < 6) {                          // ref :315-316 (lines are distinct by value, see DESIGN.md)
+                        for (int q = hit; q + 1 < qn; ++q) s.order[q] = s.order[q + 1];
+                        --qn;
+                    } else {                                 // ref :317-319: drop the three cells, keep the order
+                        int w = 0;
+                        for (int u = 0; u < llen; ++u)
+                            if (u != picked[0] && u != picked[1] && u != picked[2]) lc[w++] = lc[u];
+                        s.line_len[lj] = (uint8_t)w;
+                    }
+                } else if (len >= 3) {                       // ref :322-325
+                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
+                    have = true;
+                }
+            }
+            if (!have) continue;
+            if (name != NAME_NORMAL) {                       // ref :414-418
+                const int pos = creation_pos(mlen, ntaken, name != NAME_BOMB);
+                if (pos < 0) flags |= 2u;
+                if (pos >= 0 && ntaken < CF::ML) s.taken[ntaken++] = (uint16_t)pos;
+                if (ncq < CF::ML) {
+                    s.cq_pos[ncq] = (uint16_t)(pos < 0 ? 0xffff : pos);
+                    s.cq_type[ncq] = (int8_t)name;
+                    s.cq_colour[ncq] = (uint8_t)colour;
+                    ++ncq;
+                }
+            }
+            for (int k = 0; k < mlen; ++k) {                 // cells in resolve order (ref :421-423, :467)
+                if (nm < MCAP) out[nm++] = s.match[k];
+                else flags |= 1u;
+            }
+        }
+        return (uint32_t)nm | ((uint32_t)ncq << 16) | (flags << 24);
+    }
+
+    // resolve_colour_matches (ref :397-427) on the classified matches; all lanes
+    __device__ __forceinline__ void resolve_matches(uint32_t packed) {
+        const int nm = (int)(packed & 0xffffu), ncq = (int)((packed >> 16) & 0xffu);
+        const uint32_t flags = packed >> 24;
+        if (flags & 1u) status |= ST_LINE_OVERFLOW;
+        if (flags & 2u) status |= ST_INTERNAL;
+        const uint16_t* ml = mlist();
+        int pos = 0;
+        while (pos < nm) {                                   // ref :421-423 -> resolve_colour_match :460-471
+            auto cell_of = [&](int i) { return (int)ml[i]; };
+            const int first = first_in_order(pos, nm, [&](int i) { return not01(typ[cell_of(i)]); });
+            delete_in_order(pos, first, cell_of);
+            if (first >= nm) break;
+            const int cell = cell_of(first);
+            const int t = typ[cell];
+            sync();
+            activate(cell, t, true);
+            pos = first + 1;
+        }
+        sync();
+        for (int i = lane; i < ncq; i += L) {                // ref :426-427 -> create_special :572-597
+            if (s.cq_pos[i] == 0xffff) continue;
+            col[s.cq_pos[i]] = (int8_t)s.cq_colour[i];
+            typ[s.cq_pos[i]] = s.cq_type[i];
+        }
+        n_new += ncq;
+    }
 
     // one cascade round without gravity/refill (ref :369-373); returns the number of lines found
     __device__ int resolve_round() {
@@ -830,15 +837,106 @@ template <int L> struct Board {
         if (sc.rstar < 0) return 0;
         const int n = build_line_table(sc);
         ++prof_rounds;
-        if (lane == 0) {
-            const long long t0 = p.prof ? clock64() : 0;
-            Serial<L> q = make_serial();
-            q.process_and_resolve(n);
-            take_serial(q);
-            if (p.prof) prof_serial += (uint32_t)(clock64() - t0);
-        }
+        const long long t0 = p.prof ? clock64() : 0;
+        uint32_t packed = 0u;
+        if (lane == 0) packed = classify_lines(n);
+        packed = (uint32_t)shfl((int)packed, 0);
+        sync();
+        resolve_matches(packed);
+        if (p.prof) prof_serial += (uint32_t)(clock64() - t0);
         sync();
         return n;
+    }
+
+    // activate every cell selected by `pred`, in row-major order, re-testing live cells (ref :721-726)
+    template <typename F> __device__ __forceinline__ void activate_row_major(F&& pred) {
+        int cur = 0;
+        for (;;) {
+            sync();
+            int cand = 1 << 20;
+            if (lane < C)
+                for (int r = cur / C; r < R; ++r) {
+                    const int i = r * C + lane;
+                    if (i >= cur && pred(i)) { cand = i; break; }
+                }
+            cand = rmin(cand);
+            if (cand >= (1 << 20)) break;
+            const int t = typ[cand];
+            sync();
+            activate(cand, t, false);
+            cur = cand + 1;
+        }
+    }
+    __device__ __forceinline__ void delete_two(int i1, int i2) {
+        sync();
+        if (lane == 0) { col[i1] = 0; typ[i1] = 0; col[i2] = 0; typ[i2] = 0; }
+        sync();
+    }
+
+    // combination_match (ref :600-719); all lanes, uniform control flow
+    __device__ void combination(int i1, int i2) {
+        n_act += 2;                                          // ref :609
+        sync();
+        const int t1 = typ[i1], k1 = col[i1], t2 = typ[i2], k2 = col[i2];
+        const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
+        sync();
+        if (t1 == -1 && t2 == -1) {                          // ref :615-616
+            for (int i = lane; i < P; i += L) { col[i] = 0; typ[i] = 0; }
+        } else if ((t1 == -1 && t2 == 1) || (t1 == 1 && t2 == -1)) {  // ref :619-641
+            const int ck = (t1 == -1) ? i1 : i2;
+            const int kk = (t1 == -1) ? k2 : k1;
+            if (lane == 0) { col[ck] = 0; typ[ck] = 0; }     // ref :626,628
+            sync();
+            for (int i = lane; i < P; i += L) if (col[i] == kk && typ[i] == 1) { col[i] = 0; typ[i] = 0; }  // ref :631-635
+            // snapshot mask colour==kk & type>1, visited row-major; cells can only disappear meanwhile (ref :638-640)
+            activate_row_major([&](int i) { return col[i] == kk && typ[i] > 1; });
+            n_act -= 1;                                      // ref :641
+        } else if ((t1 == -1 && t2 >= 2) || (t1 >= 2 && t2 == -1)) {  // ref :644-660
+            const int ck = (t1 == -1) ? i1 : i2;
+            const int kk = (t1 == -1) ? k2 : k1;
+            const int tt = (t1 == -1) ? t2 : t1;
+            if (lane == 0) { col[ck] = 0; typ[ck] = 0; }     // ref :651
+            sync();
+            // ref :654 snapshot of colour==kk; a cell leaves the snapshot only by deletion (colour -> 0), and a cell
+            // that was not in it never gains the colour, so a live test of colour==kk is the same set.
+            for (int i = lane; i < P; i += L) if (col[i] == kk && typ[i] == 1) typ[i] = (int8_t)tt;  // ref :655-657
+            activate_row_major([&](int i) { return col[i] == kk && not01(typ[i]); });                 // ref :660
+        } else if ((t1 == 2 || t1 == 3) && (t2 == 2 || t2 == 3)) {    // ref :663-674
+            delete_two(i1, i2);
+            const int cell = min(r1, r2) * C + min(c1, c2);
+            activate(cell, 2, false);
+            activate(cell, 3, false);
+        } else if ((t1 == 4 && (t2 == 2 || t2 == 3)) || (t2 == 4 && (t1 == 2 || t1 == 3))) {  // ref :677-696
+            delete_two(i1, i2);
+            const int r = min(r1, r2), c = min(c1, c2);
+            const int min_r = max(r - 1, 0), max_r = min(r + 1, R - 1);
+            const int min_c = max(c - 1, 0), max_c = min(c + 1, C - 1);
+            for (int i = min_r; i <= max_r; ++i) activate(i * C + c, 3, false);
+            for (int j = min_c; j <= max_c; ++j) activate(r * C + j, 2, false);
+        } else if (t1 == 4 && t2 == 4) {                     // ref :699-719
+            delete_two(i1, i2);
+            const int r = min(r1, r2), c = min(c1, c2);
+            const int min_r = max(r - 2, 0), max_r = min(r + 2, R - 1);
+            const int min_c = max(c - 2, 0), max_c = min(c + 2, C - 1);
+            const int w = max_c - min_c + 1, n = w * (max_r - min_r + 1);
+            auto cell_of = [&](int i) { return (min_r + i / w) * C + min_c + i % w; };
+            int cur = 0;
+            while (cur < n) {   // row-major: normal -> delete, anything else that is not empty -> activate
+                sync();
+                const int first = first_in_order(cur, n, [&](int i) { const int t = typ[cell_of(i)]; return t != 1 && t != 0; });
+                for (int i = cur + lane; i < first; i += L) {
+                    const int q = cell_of(i);
+                    if (typ[q] == 1) { col[q] = 0; typ[q] = 0; }
+                }
+                if (first >= n) break;
+                const int q = cell_of(first);
+                const int t = typ[q];
+                sync();
+                activate(q, t, false);
+                cur = first + 1;
+            }
+        }
+        sync();
     }
 
     __device__ void shuffle() {
@@ -1002,11 +1100,7 @@ template <int L> struct Board {
         is_comb = comb;
         sync();  // every lane has read the swapped types before the leader starts deleting
         if (comb) {
-            if (lane == 0) {                                 // ref :361
-                Serial<L> q = make_serial();
-                q.combination(i1, i2);
-                take_serial(q);
-            }
+            combination(i1, i2);                             // ref :361
             int e_cnt;
             const int e = gravity(&e_cnt);                   // ref :362-363
             elim += e_cnt;
@@ -1020,9 +1114,7 @@ template <int L> struct Board {
             elim += e_cnt;
             refill(e);
         }
-        n_new = shfl(n_new, 0);
-        n_act = shfl(n_act, 0);
-        elim_out = elim + n_new;                             // ref :378
+        elim_out = elim + n_new;                             // ref :378 (counters are uniform across lanes)
     }
 
     __device__ bool board_is_valid() {
@@ -1071,17 +1163,17 @@ template <int L> __device__ __forceinline__ void write_step_outputs(const Params
         p.shuffled[env] = (uint8_t)shuffled;
     }
 }
-template <int L> __device__ __forceinline__ void merge_status(Board<L>& b, const Params& p) {
+template <typename B> __device__ __forceinline__ void merge_status(B& b, const Params& p) {
     const unsigned st = b.ror(b.status);
     if (st && b.lane == 0) p.status[b.env] |= st;
 }
 
 // TileMatchEnv.reset (ref tile_match_env.py:84-91) for the selected envs
-template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(const Params p) {
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(const Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     if (p.reset_mask && !p.reset_mask[gc.env]) return;
-    Board<L> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
+    Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
     b.load_cursors();
     unsigned effv = 0u, effh = 0u;
     if (p.init_boards) {
@@ -1100,11 +1192,11 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(cons
 }
 
 // TileMatchEnv.step (ref tile_match_env.py:93-112)
-template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const Params p) {
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     const int env = gc.env, lane = gc.lane;
-    Board<L> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
+    Board<L, RT, CT> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
     const long long prof_t0 = p.prof ? clock64() : 0;
     const bool want_mask = !(p.flags & FLAG_NO_MASK);
     int timer = p.timer[env];
@@ -1247,20 +1339,8 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
             break;
         }
         case OP_RESOLVE_ROUND: result = b.resolve_round(); break;
-        case OP_ACTIVATE:
-            if (lane == 0) {
-                Serial<L> q = b.make_serial();
-                q.activate(a0 * C + a1, a2, a3 == 0);
-                b.take_serial(q);
-            }
-            break;
-        case OP_COMBINE:
-            if (lane == 0) {
-                Serial<L> q = b.make_serial();
-                q.combination(a0 * C + a1, a2 * C + a3);
-                b.take_serial(q);
-            }
-            break;
+        case OP_ACTIVATE: b.activate(a0 * C + a1, a2, a3 == 0); break;
+        case OP_COMBINE: b.combination(a0 * C + a1, a2 * C + a3); break;
         case OP_MOVE: {
             int reward = 0, is_comb = 0, shuffled = 0;
             unsigned effv = 0u, effh = 0u;
@@ -1292,8 +1372,6 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
         }
         default: break;
     }
-    b.n_new = b.shfl(b.n_new, 0);
-    b.n_act = b.shfl(b.n_act, 0);
     b.store_board();
     b.store_cursors();
     merge_status(b, p);
