@@ -27,9 +27,15 @@
  * Philox4x32-10(key = (seed lo, seed hi), ctr = (k>>2 lo, k>>2 hi, e, s)).  Draws are consumed exactly
  * where the reference calls np_random.integers(1, K+1, n): row-major over the empty cells of each
  * refill (board.py:239-240), the R*C initial fill (board.py:97) and the (row+1)*C row-block redraws of
- * remove_colour_lines (board.py:129).  With refill_mode = TMG_REFILL_INJECTED the k-th colour is
- * draws[e][k] instead (pre-drawn by the caller, e.g. from numpy's PCG64, whose integers() stream is
- * contiguous across call sizes).
+ * remove_colour_lines (board.py:129).
+ * While a board is being generated (generate_board, board.py:95-112) the draws come from episode-indexed
+ * streams that start at word 0 for every board: W_reset(seed, e, j, k) = Philox(key, ctr = (k>>2, j, e, 3))[k&3]
+ * for integers() and ctr = (k>>2, j, e, 4) for shuffle(), j = number of the board (0 for the first reset).  The
+ * j-th board of an env is therefore a pure function of (seed, e, j): the library generates it ahead of time on a
+ * side stream ("pool") and tmg_step only copies it in; generating it inside tmg_step (TMG_FLAG_NO_PREGEN) gives the
+ * same bytes.  With refill_mode = TMG_REFILL_INJECTED every draw, resets included, is draws[e][k] in consumption
+ * order instead (pre-drawn by the caller, e.g. from numpy's PCG64, whose integers() stream is contiguous across
+ * call sizes), and boards are generated inside the call.
  */
 #ifndef TMG_B200_H
 #define TMG_B200_H
@@ -75,6 +81,7 @@ extern "C" {
 #define TMG_REFILL_INJECTED 1
 
 #define TMG_FLAG_NO_MASK 1u        /* do not maintain the legal-move mask in tmg_step / tmg_reset */
+#define TMG_FLAG_NO_PREGEN 2u      /* generate every board inside tmg_step instead of ahead of time on a side stream */
 
 #define TMG_MAX_ROWS 32
 #define TMG_MAX_COLS 32
@@ -116,6 +123,7 @@ typedef struct tmg_buffers {
     uint8_t *mask;                   /* [N][A]  1 = is_move_effective; all 0 on a terminal step */
     int32_t *num_moves_left;         /* [N] */
     uint32_t *status;                /* [N]  TMG_ST_* (sticky; clear with tmg_clear_status) */
+    int32_t *episode;                /* [N]  number of the current board (-1 before the first reset) */
 } tmg_buffers;
 
 int tmg_abi_version(void);
@@ -152,6 +160,10 @@ int tmg_encode_onehot(tmg_env *env, uint8_t *out_dev, void *stream);
 int tmg_encode_onehot_f32(tmg_env *env, float *out_dev, void *stream);
 
 int tmg_clear_status(tmg_env *env, void *stream);
+
+/* Makes `stream` wait for every board generation the library has queued on its side stream so far (a benchmark
+ * calls it before reading the clock; ordinary callers never need it). */
+int tmg_join(tmg_env *env, void *stream);
 
 /* TileMatchEnv.reset(seed=...) / set_seed (tile_match_env.py:79-86): new Philox key, both cursors back to 0 */
 int tmg_set_seed(tmg_env *env, uint64_t seed, void *stream);

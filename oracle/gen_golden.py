@@ -236,8 +236,13 @@ def run_trace(ref, R, C, K, cl, cs, num_moves, seed, env_id, steps, policy, init
     env.board.np_random = gen
     rng = np.random.default_rng(seed * 7919 + env_id)
     A = env.num_actions
-    if init_board is None and not dense:
+    def ref_reset():
+        gen.begin_reset()
         env.reset()
+        gen.end_reset()
+
+    if init_board is None and not dense:
+        ref_reset()
     else:
         env.board.board = (np.asarray(init_board, dtype=np.int32).copy() if init_board is not None
                            else _dense_special_board(rng, R, C, K))
@@ -270,7 +275,7 @@ def run_trace(ref, R, C, K, cl, cs, num_moves, seed, env_id, steps, policy, init
                 env.board.board = np.asarray(init_board, dtype=np.int32).copy()
                 env.timer = 0
             else:
-                env.reset()
+                ref_reset()
             mask = np.zeros(A, np.uint8)
             mask[env._get_effective_actions()] = 1
             out["resets"].append({"board": env.board.board.astype(np.int8).copy(), "mask": mask.copy(),

@@ -52,7 +52,7 @@ class _VecBuffers(C.Structure):
                 ("shuffle_cursor", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
                 ("is_combination_match", C.c_void_p), ("num_new_specials", C.c_void_p),
                 ("num_specials_activated", C.c_void_p), ("shuffled", C.c_void_p), ("mask", C.c_void_p),
-                ("num_moves_left", C.c_void_p), ("status", C.c_void_p)]
+                ("num_moves_left", C.c_void_p), ("status", C.c_void_p), ("episode", C.c_void_p)]
 
 
 _lib = None
@@ -72,6 +72,8 @@ def lib():
         "tmgo_board_set_injected": (None, [vp, vp, i64, i64]),
         "tmgo_board_get_cursors": (None, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "tmgo_board_status": (u32, [vp]),
+        "tmgo_board_set_episode": (None, [vp, i32]),
+        "tmgo_board_get_episode": (i32, [vp]),
         "tmgo_board_set": (None, [vp, vp]),
         "tmgo_board_get": (None, [vp, vp]),
         "tmgo_board_set_counters": (None, [vp, i32, i32]),
@@ -187,6 +189,13 @@ class OracleBoard:
         return self.L.tmgo_board_status(self.h)
 
     @property
+    def episode(self):
+        return self.L.tmgo_board_get_episode(self.h)
+
+    def set_episode(self, episode):
+        self.L.tmgo_board_set_episode(self.h, int(episode))
+
+    @property
     def counters(self):
         a, b = C.c_int(), C.c_int()
         self.L.tmgo_board_get_counters(self.h, C.byref(a), C.byref(b))
@@ -299,7 +308,7 @@ class OracleBoard:
 _NP = {"board": np.int8, "timer": np.int32, "draw_cursor": np.uint64, "shuffle_cursor": np.uint64,
        "reward": np.int32, "terminated": np.uint8, "is_combination_match": np.uint8,
        "num_new_specials": np.int32, "num_specials_activated": np.int32, "shuffled": np.uint8,
-       "mask": np.uint8, "num_moves_left": np.int32, "status": np.uint32}
+       "mask": np.uint8, "num_moves_left": np.int32, "status": np.uint32, "episode": np.int32}
 
 
 class OracleVecEnv:

@@ -10,6 +10,15 @@ counter-based stream so that every env can compute its k-th draw independently:
     integers(low, high, n)  -> low + mulhi32(word, high-low) for the next n words of stream 0
     shuffle(arr)            -> Fisher-Yates, i = n-1..1, j = mulhi32(next word of stream 1, i+1)
 
+While a board is being generated (TileMatchEnv.reset -> Board.generate_board, board.py:95-112) the draws come
+from episode-indexed streams instead, each starting at word 0:
+
+    reset word(seed, env_id, episode j, k)   = Philox(key, ctr = (k>>2, j, env_id, 3))[k & 3]   (integers)
+    reset shuffle word(...)                  = Philox(key, ctr = (k>>2, j, env_id, 4))[k & 3]   (shuffle)
+
+so the j-th board of an env is a pure function of (seed, env_id, j): the GPU can generate it ahead of time, off
+the step path, and the result is the same as generating it at reset time.
+
 `StreamGenerator` hands exactly this stream to the unmodified reference, which is how
 "identical refill draws" (BASELINE north_star) is realised for differential tests.
 Philox4x32-10 is the published Random123 algorithm (Salmon et al., SC'11); the
@@ -28,6 +37,8 @@ MASK32 = np.uint64(0xFFFFFFFF)
 STREAM_REFILL = 0
 STREAM_SHUFFLE = 1
 STREAM_ACTIONS = 2  # used by bench/test drivers to draw synthetic actions
+STREAM_RESET = 3
+STREAM_RESET_SHUFFLE = 4
 
 
 def philox4x32_10(ctr, key):
@@ -47,8 +58,9 @@ def philox4x32_10(ctr, key):
     return np.stack([c0, c1, c2, c3], axis=-1).astype(np.uint32)
 
 
-def stream_words(seed: int, env_id: int, stream: int, start: int, n: int) -> np.ndarray:
-    """Words start..start+n-1 of one env's stream, as uint32."""
+def stream_words(seed: int, env_id: int, stream: int, start: int, n: int, episode=None) -> np.ndarray:
+    """Words start..start+n-1 of one env's stream, as uint32.  `episode` selects an episode-indexed reset stream
+    (the episode number replaces the high half of the block counter)."""
     if n <= 0:
         return np.zeros(0, dtype=np.uint32)
     k = np.arange(start, start + n, dtype=np.uint64)
@@ -56,7 +68,7 @@ def stream_words(seed: int, env_id: int, stream: int, start: int, n: int) -> np.
     ublk, inv = np.unique(blk, return_inverse=True)
     ctr = np.zeros((len(ublk), 4), dtype=np.uint64)
     ctr[:, 0] = ublk & MASK32
-    ctr[:, 1] = ublk >> np.uint64(32)
+    ctr[:, 1] = (ublk >> np.uint64(32)) if episode is None else np.uint64(episode & 0xFFFFFFFF)
     ctr[:, 2] = np.uint64(env_id & 0xFFFFFFFF)
     ctr[:, 3] = np.uint64(stream & 0xFFFFFFFF)
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint64)
@@ -83,11 +95,28 @@ class StreamGenerator:
         self.shuffle_cursor = 0
         self.draws = None if draws is None else np.asarray(draws).reshape(-1)
         self.exhausted = False
+        self.episode = -1          # number of the board being / last generated
+        self.in_reset = False
+        self._rdc = self._rsc = 0  # cursors of the current episode's reset streams
+
+    def begin_reset(self):
+        """Call right before the reference's generate_board (env.reset); injected mode has one sequential stream."""
+        self.episode += 1
+        self.in_reset = self.draws is None
+        self._rdc = self._rsc = 0
+
+    def end_reset(self):
+        self.in_reset = False
 
     def integers(self, low, high=None, size=None):
         if high is None:
             low, high = 0, low
         n = 1 if size is None else int(np.prod(size))
+        if self.in_reset:
+            w = stream_words(self.seed, self.env_id, STREAM_RESET, self._rdc, n, episode=self.episode)
+            self._rdc += n
+            out = int(low) + mulhi32(w, int(high) - int(low))
+            return int(out[0]) if size is None else out.reshape(size)
         if self.draws is None:
             w = stream_words(self.seed, self.env_id, STREAM_REFILL, self.draw_cursor, n)
             out = int(low) + mulhi32(w, int(high) - int(low))
@@ -105,8 +134,12 @@ class StreamGenerator:
         n = len(arr)
         if n <= 1:
             return
-        w = stream_words(self.seed, self.env_id, STREAM_SHUFFLE, self.shuffle_cursor, n - 1)
-        self.shuffle_cursor += n - 1
+        if self.in_reset:
+            w = stream_words(self.seed, self.env_id, STREAM_RESET_SHUFFLE, self._rsc, n - 1, episode=self.episode)
+            self._rsc += n - 1
+        else:
+            w = stream_words(self.seed, self.env_id, STREAM_SHUFFLE, self.shuffle_cursor, n - 1)
+            self.shuffle_cursor += n - 1
         t = 0
         for i in range(n - 1, 0, -1):
             j = int((int(w[t]) * (i + 1)) >> 32)

@@ -40,6 +40,10 @@ struct tmgo_board {
     uint64_t seed;
     uint32_t env_id;
     uint64_t draw_cursor, shuffle_cursor;
+    /* episode-indexed reset streams (oracle/stream.py): board j of an env is a pure function of (seed, env, j) */
+    int32_t episode;
+    int in_reset;
+    uint64_t rdc, rsc;
     const uint8_t *inj;
     int64_t inj_len;
     int use_inj;
@@ -83,6 +87,14 @@ uint32_t tmgo_stream_word(uint64_t seed, uint32_t env_id, uint32_t stream, uint6
     return out[k & 3];
 }
 
+static uint32_t reset_word(tmgo_board *b, uint32_t stream, uint64_t k) {
+    uint32_t ctr[4] = {(uint32_t)(k >> 2), (uint32_t)b->episode, b->env_id, stream};
+    uint32_t key[2] = {(uint32_t)b->seed, (uint32_t)(b->seed >> 32)};
+    uint32_t out[4];
+    tmgo_philox4x32_10(ctr, key, out);
+    return out[k & 3];
+}
+
 static uint32_t board_word(tmgo_board *b, uint32_t stream, uint64_t k) {
     uint64_t blk = k >> 2;
     int s = stream & 1;
@@ -98,6 +110,14 @@ static uint32_t board_word(tmgo_board *b, uint32_t stream, uint64_t k) {
 
 /* np_random.integers(1, K+1, size=n) on the project stream (ref board.py:97,129,239) */
 static void draw_colours(tmgo_board *b, int n, int32_t *out) {
+    if (b->in_reset) {
+        for (int i = 0; i < n; i++) {
+            uint32_t w = reset_word(b, 3, b->rdc + (uint64_t)i);
+            out[i] = 1 + (int32_t)(((uint64_t)w * (uint64_t)b->K) >> 32);
+        }
+        b->rdc += (uint64_t)n;
+        return;
+    }
     for (int i = 0; i < n; i++) {
         if (b->use_inj) {
             int64_t k = (int64_t)b->draw_cursor + i;
@@ -157,6 +177,7 @@ static void line_sort(line_t *a) { /* sorted(key=(row,col)) == ascending cell co
 tmgo_board *tmgo_board_create(int R, int C, int K, uint32_t specials) {
     if (R < 1 || C < 1 || R > MAXDIM || C > MAXDIM) return NULL;
     tmgo_board *b = (tmgo_board *)calloc(1, sizeof(*b));
+    b->episode = -1;
     b->R = R; b->C = C; b->K = K; b->P = R * C; /* flat_size, ref board.py:56 */
     b->specials = specials;
     b->colour = (int32_t *)calloc((size_t)b->P, 4);
@@ -188,6 +209,8 @@ void tmgo_board_set_injected(tmgo_board *b, const uint8_t *draws, int64_t len, i
     b->inj = draws; b->inj_len = len; b->use_inj = draws != NULL;
     if (draws) b->draw_cursor = (uint64_t)cursor;
 }
+void tmgo_board_set_episode(tmgo_board *b, int32_t episode) { b->episode = episode; }
+int32_t tmgo_board_get_episode(const tmgo_board *b) { return b->episode; }
 void tmgo_board_get_cursors(const tmgo_board *b, uint64_t *dc, uint64_t *sc) { *dc = b->draw_cursor; *sc = b->shuffle_cursor; }
 uint32_t tmgo_board_status(const tmgo_board *b) { return b->status; }
 void tmgo_board_set(tmgo_board *b, const int32_t *planes) {
@@ -755,7 +778,7 @@ void tmgo_shuffle(tmgo_board *b) {                  /* ref board.py:114-118 with
     int32_t *idx = b->tmp;
     for (int i = 0; i < P; i++) idx[i] = i;
     for (int i = P - 1; i >= 1; i--) {
-        uint32_t w = board_word(b, 1, b->shuffle_cursor++);
+        uint32_t w = b->in_reset ? reset_word(b, 4, b->rsc++) : board_word(b, 1, b->shuffle_cursor++);
         int j = (int)(((uint64_t)w * (uint64_t)(i + 1)) >> 32);
         int32_t t = idx[i]; idx[i] = idx[j]; idx[j] = t;
     }
@@ -803,10 +826,14 @@ static int playability_loop(tmgo_board *b, int have_lines) {
 }
 
 void tmgo_generate_board(tmgo_board *b) {           /* ref board.py:95-112 */
+    b->episode++;
+    b->in_reset = !b->use_inj;                      /* injected draws are one sequential stream */
+    b->rdc = b->rsc = 0;
     for (int i = 0; i < b->P; i++) b->type[i] = 1;
     draw_colours(b, b->P, b->colour);
     get_colour_lines(b);
     playability_loop(b, 1);
+    b->in_reset = 0;
 }
 
 /* -------------------------------------------------------------------------------------------- */
@@ -901,6 +928,8 @@ tmgo_vec *tmgo_vec_create(const tmgo_vec_config *cfg) {
     for (int i = 0; i < N; i++) v->buf.timer[i] = -1; /* tile_match_env.py:75 timer = None */
     v->buf.draw_cursor = (uint64_t *)calloc((size_t)N, 8);
     v->buf.shuffle_cursor = (uint64_t *)calloc((size_t)N, 8);
+    v->buf.episode = (int32_t *)malloc(4 * (size_t)N);
+    for (int i = 0; i < N; i++) v->buf.episode[i] = -1;
     v->buf.reward = (int32_t *)calloc((size_t)N, 4);
     v->buf.terminated = (uint8_t *)calloc((size_t)N, 1);
     v->buf.is_combination_match = (uint8_t *)calloc((size_t)N, 1);
@@ -919,6 +948,7 @@ tmgo_vec *tmgo_vec_create(const tmgo_vec_config *cfg) {
 }
 void tmgo_vec_destroy(tmgo_vec *v) {
     if (!v) return;
+    free(v->buf.episode);
     free(v->buf.board); free(v->buf.timer); free(v->buf.draw_cursor); free(v->buf.shuffle_cursor);
     free(v->buf.reward); free(v->buf.terminated); free(v->buf.is_combination_match);
     free(v->buf.num_new_specials); free(v->buf.num_specials_activated); free(v->buf.shuffled);
@@ -935,6 +965,8 @@ static void load_env(tmgo_vec *v, tmgo_board *b, int e) {
     const int8_t *src = v->buf.board + (size_t)e * 2 * (size_t)P;
     for (int i = 0; i < P; i++) { b->colour[i] = src[i]; b->type[i] = src[P + i]; }
     tmgo_board_set_stream(b, v->cfg.seed, (uint32_t)(v->cfg.env_id_offset + (uint64_t)e), v->buf.draw_cursor[e], v->buf.shuffle_cursor[e]);
+    b->episode = v->buf.episode[e];
+    b->in_reset = 0;
     if (v->cfg.refill_mode == 1) {
         b->inj = v->inj ? v->inj + (size_t)e * (size_t)v->inj_len : NULL;
         b->inj_len = v->inj ? v->inj_len : 0;
@@ -950,6 +982,7 @@ static void store_env(tmgo_vec *v, tmgo_board *b, int e) {
     for (int i = 0; i < P; i++) { dst[i] = (int8_t)b->colour[i]; dst[P + i] = (int8_t)b->type[i]; }
     v->buf.draw_cursor[e] = b->draw_cursor;
     v->buf.shuffle_cursor[e] = b->shuffle_cursor;
+    v->buf.episode[e] = b->episode;
     v->buf.status[e] |= b->status;
 }
 static int board_is_valid(const tmgo_board *b) {    /* full board of (1..K, 1..4) tiles or (0,-1) cookies */

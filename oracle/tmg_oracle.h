@@ -51,6 +51,9 @@ void tmgo_board_set_stream(tmgo_board *b, uint64_t seed, uint32_t env_id, uint64
                            uint64_t shuffle_cursor);
 void tmgo_board_set_injected(tmgo_board *b, const uint8_t *draws, int64_t len, int64_t cursor);
 void tmgo_board_get_cursors(const tmgo_board *b, uint64_t *draw_cursor, uint64_t *shuffle_cursor);
+/* number of the last generated board (-1 before the first generate_board); selects the reset streams */
+void tmgo_board_set_episode(tmgo_board *b, int32_t episode);
+int32_t tmgo_board_get_episode(const tmgo_board *b);
 uint32_t tmgo_board_status(const tmgo_board *b);
 /* board I/O as int32 [2][R][C], the reference's dtype (board.py:96) */
 void tmgo_board_set(tmgo_board *b, const int32_t *planes);
@@ -119,6 +122,7 @@ typedef struct tmgo_vec_buffers { /* host arrays owned by the oracle, SoA over e
     uint8_t *mask;            /* [N][A] */
     int32_t *num_moves_left;  /* [N] */
     uint32_t *status;         /* [N], sticky */
+    int32_t *episode;         /* [N] number of the current board (-1 before the first reset) */
 } tmgo_vec_buffers;
 
 tmgo_vec *tmgo_vec_create(const tmgo_vec_config *cfg);

@@ -21,11 +21,11 @@ class _Cfg(C.Structure):
 
 
 _FIELDS = ["board", "timer", "draw_cursor", "shuffle_cursor", "reward", "terminated", "is_combination_match",
-           "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status"]
+           "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status", "episode"]
 _NP = {"board": np.int8, "timer": np.int32, "draw_cursor": np.uint64, "shuffle_cursor": np.uint64, "reward": np.int32,
        "terminated": np.uint8, "is_combination_match": np.uint8, "num_new_specials": np.int32,
        "num_specials_activated": np.int32, "shuffled": np.uint8, "mask": np.uint8, "num_moves_left": np.int32,
-       "status": np.uint32}
+       "status": np.uint32, "episode": np.int32}
 
 
 class _Bufs(C.Structure):

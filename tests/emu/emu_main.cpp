@@ -120,6 +120,12 @@ template <int L> static void e_step() {
     else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_step<32, 32, 32>(g_params);
     else k_step<L, 0, 0>(g_params);
 }
+template <int L> static void e_pregen() {
+    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_pregen<16, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_pregen<16, 9, 9>(g_params);
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_pregen<32, 32, 32>(g_params);
+    else k_pregen<L, 0, 0>(g_params);
+}
 template <int L> static void e_mask() { k_mask<L>(g_params); }
 template <int L> static void e_debug() { k_debug<L>(g_params); }
 
@@ -154,7 +160,7 @@ struct emu_config {
 };
 struct emu_buffers {
     void *board, *timer, *draw_cursor, *shuffle_cursor, *reward, *terminated, *is_combination_match, *num_new_specials,
-        *num_specials_activated, *shuffled, *mask, *num_moves_left, *status;
+        *num_specials_activated, *shuffled, *mask, *num_moves_left, *status, *episode;
 };
 
 void* emu_create(const emu_config* c) {
@@ -171,8 +177,9 @@ void* emu_create(const emu_config* c) {
     const size_t N = (size_t)p.N;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
-    size_t o[13] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
-                    take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4)};
+    size_t o[18] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
+                    take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4), take(N * 4), take(N * 4),
+                    take(N * 2 * p.P), take(N * p.A), take(N * 4)};
     e->mem.assign(off + 256, 0);
     char* b = e->mem.data();
     b += (256 - ((uintptr_t)b & 255)) & 255;
@@ -181,7 +188,9 @@ void* emu_create(const emu_config* c) {
     p.is_comb = (uint8_t*)(b + o[6]); p.new_specials = (int32_t*)(b + o[7]); p.activated = (int32_t*)(b + o[8]);
     p.shuffled = (uint8_t*)(b + o[9]); p.mask = (uint8_t*)(b + o[10]); p.moves_left = (int32_t*)(b + o[11]);
     p.status = (uint32_t*)(b + o[12]);
-    for (size_t i = 0; i < N; ++i) p.timer[i] = -1;
+    p.episode = (int32_t*)(b + o[13]); p.pool_episode = (int32_t*)(b + o[14]);
+    p.pool_board = (int8_t*)(b + o[15]); p.pool_mask = (uint8_t*)(b + o[16]); p.pool_status = (uint32_t*)(b + o[17]);
+    for (size_t i = 0; i < N; ++i) { p.timer[i] = -1; p.episode[i] = -1; p.pool_episode[i] = (int32_t)0x80808080; }
     return e;
 }
 void emu_destroy(void* h) { delete (EmuEnv*)h; }
@@ -190,7 +199,7 @@ void emu_get_buffers(void* h, emu_buffers* o) {
     o->board = p.board; o->timer = p.timer; o->draw_cursor = p.draw_cursor; o->shuffle_cursor = p.shuffle_cursor;
     o->reward = p.reward; o->terminated = p.terminated; o->is_combination_match = p.is_comb;
     o->num_new_specials = p.new_specials; o->num_specials_activated = p.activated; o->shuffled = p.shuffled;
-    o->mask = p.mask; o->num_moves_left = p.moves_left; o->status = p.status;
+    o->mask = p.mask; o->num_moves_left = p.moves_left; o->status = p.status; o->episode = p.episode;
 }
 void emu_set_injected_draws(void* h, const uint8_t* d, int64_t len) { ((EmuEnv*)h)->p.inj = d; ((EmuEnv*)h)->p.inj_len = len; }
 
@@ -205,11 +214,13 @@ void emu_reset(void* h, const uint8_t* reset_mask, const int8_t* init_boards) {
     EmuEnv* e = (EmuEnv*)h;
     g_params = e->p; g_params.reset_mask = reset_mask; g_params.init_boards = init_boards;
     DISPATCH(e_reset)
+    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; DISPATCH(e_pregen) }
 }
 void emu_step(void* h, const int32_t* actions) {
     EmuEnv* e = (EmuEnv*)h;
     g_params = e->p; g_params.actions = actions;
     DISPATCH(e_step)
+    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; DISPATCH(e_pregen) }
 }
 void emu_legal_mask(void* h) {
     EmuEnv* e = (EmuEnv*)h;

@@ -52,6 +52,7 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline long long clock64() { return 0; }
+static inline void __threadfence() {}
 using std::max;
 using std::min;
 

@@ -24,15 +24,18 @@ def test_golden_traces_through_emulated_device_code():
     (9, 9, 6, ALL_CL, ALL_CS, 8, "next_step", 24, 30),
     (4, 5, 3, ALL_CL, ALL_CS, 5, "same_step", 48, 40),
     (6, 20, 5, ALL_CL, ALL_CS, 6, "same_step", 8, 20),
+    (10, 10, 4, ALL_CL, ALL_CS, 5, "same_step", 16, 12, 2),   # TMG_FLAG_NO_PREGEN: boards generated inside the step
+    (3, 5, 3, ALL_CL, ALL_CS, 3, "same_step", 64, 30),        # tiny boards: shuffles inside generate_board
 ])
 def test_emulated_batch_vs_oracle(cfg):
-    R, C, K, cl, cs, moves, autoreset, N, steps = cfg
-    e = EmuVecEnv(N, R, C, K, moves, cl, cs, seed=3, autoreset=autoreset, env_id_offset=50)
+    R, C, K, cl, cs, moves, autoreset, N, steps = cfg[:9]
+    flags = cfg[9] if len(cfg) > 9 else 0
+    e = EmuVecEnv(N, R, C, K, moves, cl, cs, seed=3, autoreset=autoreset, env_id_offset=50, flags=flags)
     o = orc.OracleVecEnv(N, R, C, K, moves, cl, cs, seed=3, autoreset=autoreset, env_id_offset=50, num_threads=4)
     e.reset(); o.reset()
     rng = np.random.default_rng(7)
     fields = ["board", "timer", "draw_cursor", "shuffle_cursor", "reward", "terminated", "is_combination_match",
-              "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status"]
+              "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status", "episode"]
     for t in range(steps):
         m = o.mask.astype(np.float64) + 1e-9
         u = rng.random((N, 1)) * m.sum(axis=1, keepdims=True)

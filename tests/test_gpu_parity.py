@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ALL_CL = ("cookie",)
 ALL_CS = ("vertical_laser", "horizontal_laser", "bomb")
 FIELDS = ["board", "timer", "draw_cursor", "shuffle_cursor", "reward", "terminated", "is_combination_match",
-          "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status"]
+          "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status", "episode"]
 
 
 def _torch():

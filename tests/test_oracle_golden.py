@@ -277,7 +277,14 @@ def test_live_differential_fuzz_against_reference(cfg):
         env.board.np_random = StreamGenerator(11, env_id)
         o = orc.OracleVecEnv(1, R, C, K, nm, cl, cs, seed=11, env_id_offset=env_id)
         rng = np.random.default_rng(env_id)
-        _, info = env.reset(); o.reset()
+
+        def ref_reset():   # generate_board draws come from the episode-indexed reset streams (oracle/stream.py)
+            env.board.np_random.begin_reset()
+            out = env.reset()
+            env.board.np_random.end_reset()
+            return out
+
+        _, info = ref_reset(); o.reset()
         for t in range(150):
             assert np.array_equal(env.board.board.astype(np.int8), o.board[0])
             m = np.zeros(o.A, np.uint8); m[info["effective_actions"]] = 1
@@ -290,4 +297,4 @@ def test_live_differential_fuzz_against_reference(cfg):
             assert int(info["num_specials_activated"]) == int(o.num_specials_activated[0])
             assert env.board.np_random.draw_cursor == int(o.draw_cursor[0])
             if done:
-                _, info = env.reset(); o.reset()
+                _, info = ref_reset(); o.reset()

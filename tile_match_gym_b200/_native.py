@@ -22,6 +22,7 @@ SPECIAL_BITS = {"cookie": SP_COOKIE, "vertical_laser": SP_VERTICAL_LASER,
 AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
 REFILL = {"philox": 0, "injected": 1}
 FLAG_NO_MASK = 1
+FLAG_NO_PREGEN = 2
 
 ST_BAD_ACTION, ST_NEEDS_RESET, ST_DRAWS_EXHAUSTED, ST_RESET_CAP = 1, 2, 4, 8
 ST_LINE_OVERFLOW, ST_DFS_OVERFLOW, ST_INVALID_BOARD, ST_INTERNAL = 16, 32, 64, 128
@@ -40,7 +41,7 @@ class Config(C.Structure):
 
 BUFFER_FIELDS = ["board", "timer", "draw_cursor", "shuffle_cursor", "reward", "terminated",
                  "is_combination_match", "num_new_specials", "num_specials_activated", "shuffled", "mask",
-                 "num_moves_left", "status"]
+                 "num_moves_left", "status", "episode"]
 
 
 class Buffers(C.Structure):
@@ -72,6 +73,7 @@ EXPORTS = {
     "tmg_encode_onehot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_clear_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tmg_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "tmg_step_host": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_void_p]),
     "tmg_set_profile_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),

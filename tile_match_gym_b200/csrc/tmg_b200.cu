@@ -20,6 +20,12 @@ struct tmg_env {
     int32_t* actions_dev;  // staging for tmg_step_host
     void* base;     // one allocation backs every buffer
     size_t bytes;
+    // board pool: k_pregen runs on a side stream so that generate_board stays off the step path
+    cudaStream_t side;
+    static constexpr int RING = 16;
+    cudaEvent_t ev_step, ev_pregen[RING];
+    long long pregen_count;   // number of k_pregen launches so far
+    bool pregen;              // pool in use (philox refill, not disabled by flag)
 };
 
 namespace {
@@ -68,6 +74,29 @@ int last_error() { return cudaGetLastError() == cudaSuccess ? TMG_OK : TMG_ERR_C
 template <int L> int grid_for(int n) { return (n + Cfg<L>::GPB - 1) / Cfg<L>::GPB; }
 
 }  // namespace
+
+// `st` waits until every k_pregen launched so far has finished (used by the rare calls that rewrite env state)
+static bool join_pregen(tmg_env* e, cudaStream_t st) {
+    if (!e->pregen || e->pregen_count == 0) return true;
+    return cudaStreamWaitEvent(st, e->ev_pregen[(e->pregen_count - 1) % tmg_env::RING], 0) == cudaSuccess;
+}
+// after a kernel on `st` that may have consumed pool entries: refill them on the side stream
+static int launch_pregen(tmg_env* e, cudaStream_t st) {
+    if (!e->pregen) return TMG_OK;
+    if (cudaEventRecord(e->ev_step, st) != cudaSuccess) return TMG_ERR_CUDA;
+    if (cudaStreamWaitEvent(e->side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
+    const Params p = e->p;
+    const int rc = launch_by_shape(e, [&](auto shape) {
+        typedef decltype(shape) S;
+        constexpr int L = S::L;
+        k_pregen<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), e->side>>>(p);
+        return last_error();
+    });
+    if (rc != TMG_OK) return rc;
+    if (cudaEventRecord(e->ev_pregen[e->pregen_count % tmg_env::RING], e->side) != cudaSuccess) return TMG_ERR_CUDA;
+    ++e->pregen_count;
+    return TMG_OK;
+}
 
 extern "C" {
 
@@ -157,7 +186,9 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_sc = take((size_t)N * 8), o_rew = take((size_t)N * 4), o_term = take(N), o_comb = take(N),
                  o_new = take((size_t)N * 4), o_act = take((size_t)N * 4), o_shuf = take(N),
                  o_mask = take((size_t)N * p.A), o_left = take((size_t)N * 4), o_stat = take((size_t)N * 4),
-                 o_actions = take((size_t)N * 4);
+                 o_actions = take((size_t)N * 4), o_ep = take((size_t)N * 4), o_pool_ep = take((size_t)N * 4),
+                 o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
+                 o_pool_status = take((size_t)N * 4);
     e->bytes = off;
     if (cudaMalloc(&e->base, e->bytes) != cudaSuccess) { cudaGetLastError(); delete e; return TMG_ERR_OOM; }
     if (cudaMemset(e->base, 0, e->bytes) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
@@ -176,6 +207,22 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.moves_left = reinterpret_cast<int32_t*>(b + o_left);
     p.status = reinterpret_cast<uint32_t*>(b + o_stat);
     e->actions_dev = reinterpret_cast<int32_t*>(b + o_actions);
+    p.episode = reinterpret_cast<int32_t*>(b + o_ep);
+    p.pool_episode = reinterpret_cast<int32_t*>(b + o_pool_ep);
+    p.pool_board = reinterpret_cast<int8_t*>(b + o_pool_board);
+    p.pool_mask = reinterpret_cast<uint8_t*>(b + o_pool_mask);
+    p.pool_status = reinterpret_cast<uint32_t*>(b + o_pool_status);
+    e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
+    e->pregen_count = 0;
+    e->side = nullptr;
+    bool ok = cudaMemset(p.episode, 0xff, (size_t)N * 4) == cudaSuccess &&       // -1: no board generated yet
+              cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess;    // never equal to a real episode
+    if (e->pregen) {
+        ok = ok && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < tmg_env::RING; ++i) ok = ok && cudaEventCreateWithFlags(&e->ev_pregen[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
     // timer = -1: "reset has never been called" (tile_match_env.py:75)
     if (cudaMemset(p.timer, 0xff, (size_t)N * 4) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
     if (cudaDeviceSynchronize() != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
@@ -186,6 +233,12 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
 int tmg_destroy(tmg_env* e) {
     if (!e) return TMG_ERR_INVALID_ARG;
     cudaSetDevice(e->cfg.device);
+    if (e->pregen) {
+        cudaStreamSynchronize(e->side);
+        cudaEventDestroy(e->ev_step);
+        for (int i = 0; i < tmg_env::RING; ++i) cudaEventDestroy(e->ev_pregen[i]);
+        cudaStreamDestroy(e->side);
+    }
     cudaFree(e->base);
     delete e;
     return TMG_OK;
@@ -197,7 +250,7 @@ int tmg_get_buffers(tmg_env* e, tmg_buffers* out) {
     out->board = p.board; out->timer = p.timer; out->draw_cursor = p.draw_cursor; out->shuffle_cursor = p.shuffle_cursor;
     out->reward = p.reward; out->terminated = p.terminated; out->is_combination_match = p.is_comb;
     out->num_new_specials = p.new_specials; out->num_specials_activated = p.activated; out->shuffled = p.shuffled;
-    out->mask = p.mask; out->num_moves_left = p.moves_left; out->status = p.status;
+    out->mask = p.mask; out->num_moves_left = p.moves_left; out->status = p.status; out->episode = p.episode;
     return TMG_OK;
 }
 
@@ -217,12 +270,15 @@ int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boar
     p.init_boards = init_boards_dev;
     p.init_vecw = init_boards_dev ? ptr_vec_width(init_boards_dev, p.board_vecw) : p.board_vecw;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return launch_by_shape(e, [&](auto shape) {
+    if (!join_pregen(e, st)) return TMG_ERR_CUDA;
+    const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
         k_reset<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
+    if (rc != TMG_OK) return rc;
+    return launch_pregen(e, st);
 }
 
 int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
@@ -231,12 +287,22 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
     Params p = e->p;
     p.actions = actions_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return launch_by_shape(e, [&](auto shape) {
+    if (e->pregen) {
+        // An env consumes its pool entry at most once per episode, so the refill launched W steps ago (W <= num_moves)
+        // is the latest one this step can depend on; everything newer keeps running beside the step kernels.
+        const long long W = p.num_moves < 8 ? p.num_moves : 8;
+        if (e->pregen_count >= W &&
+            cudaStreamWaitEvent(st, e->ev_pregen[(e->pregen_count - W) % tmg_env::RING], 0) != cudaSuccess)
+            return TMG_ERR_CUDA;
+    }
+    const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
         k_step<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
+    if (rc != TMG_OK) return rc;
+    return launch_pregen(e, st);
 }
 
 int tmg_legal_mask(tmg_env* e, void* stream) {
@@ -275,10 +341,18 @@ int tmg_clear_status(tmg_env* e, void* stream) {
     return last_error();
 }
 
+int tmg_join(tmg_env* e, void* stream) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    return join_pregen(e, static_cast<cudaStream_t>(stream)) ? TMG_OK : TMG_ERR_CUDA;
+}
+
 int tmg_set_seed(tmg_env* e, uint64_t seed, void* stream) {
     if (!e) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!join_pregen(e, st)) return TMG_ERR_CUDA;
+    if (cudaMemsetAsync(e->p.episode, 0xff, (size_t)e->p.N * 4, st) != cudaSuccess) return TMG_ERR_CUDA;
+    if (cudaMemsetAsync(e->p.pool_episode, 0x80, (size_t)e->p.N * 4, st) != cudaSuccess) return TMG_ERR_CUDA;
     e->cfg.seed = seed;
     e->p.key0 = (uint32_t)seed;
     e->p.key1 = (uint32_t)(seed >> 32);
@@ -327,6 +401,7 @@ int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) 
     p.dbg_op = op;
     p.dbg_args = args_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!join_pregen(e, st)) return TMG_ERR_CUDA;
     return launch_by_lanes(e, [&](auto lanes) {
         constexpr int L = decltype(lanes)::value;
         k_debug<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);

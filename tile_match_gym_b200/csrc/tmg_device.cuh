@@ -40,7 +40,7 @@ enum : uint32_t {
 };
 enum : uint32_t { SP_COOKIE = 1u, SP_VLASER = 2u, SP_HLASER = 4u, SP_BOMB = 8u };
 enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 };
-enum : uint32_t { FLAG_NO_MASK = 1u };
+enum : uint32_t { FLAG_NO_MASK = 1u, FLAG_NO_PREGEN = 2u };
 enum { OP_GRAVITY = 1, OP_REFILL, OP_RESOLVE_ROUND, OP_ACTIVATE, OP_COMBINE, OP_MOVE, OP_EFFECTIVE, OP_GENERATE,
        OP_SHUFFLE, OP_COUNT_LINES };
 enum { NAME_NORMAL = 0, NAME_VLASER = 2, NAME_HLASER = 3, NAME_BOMB = 4, NAME_COOKIE = -1 };  // = created tile type
@@ -70,6 +70,11 @@ struct Params {
     uint32_t* status;
     const uint8_t* inj;
     long long inj_len;
+    int32_t* episode;        // [N] number of the current board, -1 before the first generate_board
+    int8_t* pool_board;      // [N][2][R][C] the NEXT board of each env, generated ahead of time (k_pregen)
+    uint8_t* pool_mask;      // [N][A]       its legal-move mask
+    int32_t* pool_episode;   // [N]          which episode the pool entry belongs to (-1 = none)
+    uint32_t* pool_status;   // [N]          status bits raised while generating it (merged when it is consumed)
     // per-call inputs
     const int32_t* actions;
     const uint8_t* reset_mask;
@@ -197,15 +202,17 @@ __device__ __noinline__ MaskPair mask_literal_column(const int8_t* col, const in
 
 // shuffle (ref :114-118): new[i] = old[perm[i]], perm = Fisher-Yates of arange(P) on stream 1.  Applying the
 // same swaps to the cells themselves yields exactly old[perm[i]].  One lane.
+// `episode` >= 0 selects the reset shuffle stream of that board (ctr = (blk, episode, env, 4)).
 __device__ __noinline__ void shuffle_serial(int8_t* col, int8_t* typ, int P, uint32_t gid, uint32_t key0, uint32_t key1,
-                                            uint64_t scur) {
+                                            uint64_t scur, long long episode) {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     uint64_t have_blk = ~0ull;
     for (int i = P - 1; i >= 1; --i) {
         const uint64_t k = scur++;
         const uint64_t blk = k >> 2;
         if (blk != have_blk) {
-            philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), gid, 1u, key0, key1, w);
+            if (episode >= 0) philox4x32_10((uint32_t)blk, (uint32_t)episode, gid, 4u, key0, key1, w);
+            else philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), gid, 1u, key0, key1, w);
             have_blk = blk;
         }
         const uint32_t word = (k & 3) == 0 ? w[0] : (k & 3) == 1 ? w[1] : (k & 3) == 2 ? w[2] : w[3];
@@ -236,6 +243,10 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     uint32_t status;
     int n_new, n_act;  // counters, uniform after broadcast (ref :343-344)
     uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
+    // While a board is generated the draws come from the episode-indexed reset streams (see include/tmg_b200.h):
+    bool in_reset = false;
+    uint32_t episode = 0u;
+    uint64_t rdc = 0ull, rsc = 0ull;
 
     __device__ Board(GroupSmem<L>& sm, const Params& pp, int lane_, unsigned gmask_, int gshift_, int env_)
         : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(RT ? RT : pp.R), C(CT ? CT : pp.C),
@@ -319,11 +330,12 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         if (p.use_inj) {
             for (int i = lane; i < n; i += L) col[i] = (int8_t)injected_colour(i);
         } else {
-            const uint64_t b0 = dcur >> 2, b1 = (dcur + (uint64_t)n - 1) >> 2;
+            const uint64_t cur = in_reset ? rdc : dcur;
+            const uint64_t b0 = cur >> 2, b1 = (cur + (uint64_t)n - 1) >> 2;
             for (uint64_t b = b0 + (uint64_t)lane; b <= b1; b += L) {
                 uint32_t w[4];
-                philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, 0u, p.key0, p.key1, w);
-                const int base = (int)((long long)(b << 2) - (long long)dcur);
+                philox4x32_10((uint32_t)b, in_reset ? episode : (uint32_t)(b >> 32), gid, in_reset ? 3u : 0u, p.key0, p.key1, w);
+                const int base = (int)((long long)(b << 2) - (long long)cur);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int idx = base + i;
@@ -331,7 +343,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                 }
             }
         }
-        dcur += (uint64_t)n;
+        if (in_reset) rdc += (uint64_t)n;
+        else dcur += (uint64_t)n;
         sync();
     }
 
@@ -941,8 +954,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
 
     __device__ void shuffle() {
         sync();
-        if (lane == 0) shuffle_serial(col, typ, P, gid, p.key0, p.key1, scur);
-        scur += (uint64_t)(P > 1 ? P - 1 : 0);  // one word per Fisher-Yates step, on every lane
+        if (lane == 0) shuffle_serial(col, typ, P, gid, p.key0, p.key1, in_reset ? rsc : scur, in_reset ? (long long)episode : -1ll);
+        if (in_reset) rsc += (uint64_t)(P > 1 ? P - 1 : 0);  // one word per Fisher-Yates step, on every lane
+        else scur += (uint64_t)(P > 1 ? P - 1 : 0);
         sync();
     }
 
@@ -1117,6 +1131,15 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         elim_out = elim + n_new;                             // ref :378 (counters are uniform across lanes)
     }
 
+    // generate_board (ref :95-112) for board number `ep` of this env: a pure function of (seed, env, ep)
+    __device__ __forceinline__ void begin_generate(uint32_t ep) {
+        episode = ep;
+        in_reset = !p.use_inj;   // injected draws are one sequential stream
+        rdc = 0ull; rsc = 0ull;
+        draw_cells(P, true);     // ref :96-97
+    }
+    __device__ __forceinline__ void end_generate() { in_reset = false; }
+
     __device__ bool board_is_valid() {
         bool bad = false;
         for (int i = lane; i < P; i += L) {
@@ -1181,8 +1204,12 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         if (!b.board_is_valid()) b.status |= ST_INVALID_BOARD;
         b.mask_bits(effv, effh);
     } else {
-        b.draw_cells(p.P, true);                 // generate_board (ref board.py:95-112)
+        const int ep = p.episode[gc.env] + 1;    // generate_board (ref board.py:95-112)
+        b.sync();
+        b.begin_generate((uint32_t)ep);
         b.playability(false, true, effv, effh);
+        b.end_generate();
+        if (gc.lane == 0) p.episode[gc.env] = ep;
     }
     b.store_board();
     b.store_cursors();
@@ -1238,8 +1265,18 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
     } else {
         timer = 0;
     }
-    const bool dirty = eff || regenerate;
-    if (dirty) b.load_cursors();
+    // The next board is a pure function of (seed, env, episode): take it from the pool k_pregen filled ahead of
+    // time when it is there, generate it here otherwise (same result either way).
+    int next_ep = 0;
+    bool from_pool = false;
+    if (regenerate) {
+        next_ep = p.episode[env] + 1;
+        from_pool = !p.use_inj && p.pool_episode[env] == next_ep;
+    }
+    b.sync();
+    const bool inline_gen = regenerate && !from_pool;
+    const bool dirty = eff || inline_gen;
+    if (eff || regenerate) b.load_cursors();
     // phase 0: the move itself; phase 1: generate_board of the next episode.  One call site each.
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
@@ -1252,19 +1289,29 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             b.move_core(i1, i2, reward, is_comb);
             clean = true; all_normal = false;
         } else {
-            if (!regenerate) continue;
-            b.draw_cells(p.P, true);                                       // ref board.py:96-97
+            if (!inline_gen) continue;
+            b.begin_generate((uint32_t)next_ep);
             clean = false; all_normal = true;
         }
         const bool sh = b.playability(clean, all_normal, effv, effh);      // ref board.py:381-391 / :99-109
         if (phase == 0) shuffled = sh;
+        else b.end_generate();
     }
     const int n_new = b.n_new, n_act = b.n_act;
-    if (dirty) { b.store_board(); b.store_cursors(); }
-    if (want_mask) {
-        if (zero_mask) b.store_zero_mask();
-        else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); }
+    if (from_pool) {                       // board and mask of the new episode come straight from the pool
+        b.sync();
+        copy_bytes<L>(p.board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, 2 * p.P, p.board_vecw, lane);
+        if (want_mask) copy_bytes<L>(p.mask + (size_t)env * p.A, p.pool_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
+        b.status |= p.pool_status[env];
+        if (eff) b.store_cursors();
+    } else {
+        if (dirty) { b.store_board(); b.store_cursors(); }
+        if (want_mask) {
+            if (zero_mask) b.store_zero_mask();
+            else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); }
+        }
     }
+    if (regenerate && lane == 0) p.episode[env] = next_ep;
     merge_status(b, p);
     write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled);
     if (p.prof && lane == 0) {
@@ -1273,6 +1320,33 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         p.prof[env * 4 + 2] = b.prof_rounds;
         p.prof[env * 4 + 3] = b.prof_iters;
     }
+}
+
+// Fills the pool: for every env whose pool entry is not the board after its current one, generate that board
+// (and its mask).  Runs on a side stream, off the step path; touches no env state.
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_pregen(const Params p) {
+    const GroupCtx<L> gc;
+    if (gc.env >= p.N) return;
+    const int ep = p.episode[gc.env] + 1;
+    if (p.pool_episode[gc.env] == ep) return;
+    Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
+    unsigned effv = 0u, effh = 0u;
+    b.sync();
+    b.begin_generate((uint32_t)ep);
+    b.playability(false, true, effv, effh);
+    b.end_generate();
+    b.sync();
+    copy_bytes<L>(p.pool_board + (size_t)gc.env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, gc.lane);
+    if (!(p.flags & FLAG_NO_MASK)) {
+        b.mask_to_smem(effv, effh);
+        b.sync();
+        copy_bytes<L>(p.pool_mask + (size_t)gc.env * p.A, b.s.mask, p.A, p.mask_vecw, gc.lane);
+    }
+    const unsigned st = b.ror(b.status);
+    if (gc.lane == 0) p.pool_status[gc.env] = st;
+    __threadfence();   // the board must be visible before the entry is declared valid
+    b.sync();
+    if (gc.lane == 0) p.pool_episode[gc.env] = ep;
 }
 
 // _get_effective_actions for every env from its current board (ref tile_match_env.py:118-124)
@@ -1363,7 +1437,16 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
             result = b.shfl((int)eff, 0);
             break;
         }
-        case OP_GENERATE: { unsigned v, h; b.draw_cells(p.P, true); b.playability(false, true, v, h); break; }
+        case OP_GENERATE: {
+            unsigned v, h;
+            const int ep = p.episode[env] + 1;
+            b.sync();
+            b.begin_generate((uint32_t)ep);
+            b.playability(false, true, v, h);
+            b.end_generate();
+            if (lane == 0) p.episode[env] = ep;
+            break;
+        }
         case OP_SHUFFLE: b.shuffle(); break;
         case OP_COUNT_LINES: {
             const typename Board<L>::Scan sc = b.scan_lines(p.R - 1, false);

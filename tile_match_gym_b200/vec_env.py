@@ -33,7 +33,7 @@ class _DevArray:
 _TYPESTR = {"board": "|i1", "timer": "<i4", "draw_cursor": "<i8", "shuffle_cursor": "<i8", "reward": "<i4",
             "terminated": "|u1", "is_combination_match": "|u1", "num_new_specials": "<i4",
             "num_specials_activated": "<i4", "shuffled": "|u1", "mask": "|u1", "num_moves_left": "<i4",
-            "status": "<i4"}
+            "status": "<i4", "episode": "<i4"}
 
 
 class TileMatchVecEnv:
@@ -49,6 +49,8 @@ class TileMatchVecEnv:
       env_id_offset   global id of local env 0; the draw stream of an env depends only on (seed, global id),
                       so results are independent of how the batch is sharded over GPUs
       compute_mask    maintain info["effective_actions"] (the reference always does)
+      pregenerate     generate each env's next board ahead of time on a side stream (same bytes as generating it
+                      inside the step; only the timing differs)
       obs             "int8" (aliases engine state, zero-copy), "int32" (reference dtype, one cast per call)
                       or "onehot" (OneHotWrapper planes, uint8)
     """
@@ -59,7 +61,7 @@ class TileMatchVecEnv:
                  colourless_specials, colour_specials, seed: Optional[int] = 1, device="cuda:0",
                  autoreset: str = "next_step", refill: str = "philox", env_id_offset: int = 0,
                  compute_mask: bool = True, obs: str = "int8", max_reset_iters: int = 0,
-                 render_mode: str = "string"):
+                 render_mode: str = "string", pregenerate: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("tile_match_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = nat.lib()
@@ -92,7 +94,9 @@ class TileMatchVecEnv:
             torch.zeros(1, device=self.device)  # make sure the primary context exists before the library uses it
         cfg = nat.Config(C.sizeof(nat.Config), dev_index, self.num_envs, self.num_rows, self.num_cols,
                          self.num_colours, self.num_moves, self.specials, nat.AUTORESET[autoreset],
-                         nat.REFILL[refill], 0 if compute_mask else nat.FLAG_NO_MASK, int(max_reset_iters),
+                         nat.REFILL[refill],
+                         (0 if compute_mask else nat.FLAG_NO_MASK) | (0 if pregenerate else nat.FLAG_NO_PREGEN),
+                         int(max_reset_iters),
                          self.seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset)
         h = C.c_void_p()
         nat.check(self._lib.tmg_create(C.byref(cfg), C.byref(h)), "tmg_create")
@@ -119,6 +123,7 @@ class TileMatchVecEnv:
         self.mask = self._t["mask"].view(torch.bool)
         self.num_moves_left = self._t["num_moves_left"]
         self.status = self._t["status"]
+        self.episode = self._t["episode"]
         self.truncated = torch.zeros(N, dtype=torch.bool, device=self.device)  # tile_match_env.py:112: always False
         self._onehot = (torch.empty((N, self.onehot_planes, R, Cc), dtype=torch.uint8, device=self.device)
                         if obs == "onehot" else None)
@@ -237,6 +242,10 @@ class TileMatchVecEnv:
             "effective_actions": self.mask,
         }
         return self._obs(), self.reward, self.terminated, self.truncated, info
+
+    def join(self) -> None:
+        """Make the current stream wait for the board generations queued on the library's side stream."""
+        nat.check(self._lib.tmg_join(self._h, self._stream()), "tmg_join")
 
     def legal_mask(self) -> torch.Tensor:
         """Recompute the mask from the current boards (tile_match_env.py:118-124)."""
