@@ -8,9 +8,10 @@ A "step" is one TileMatchEnv.step over the whole batch of synthetic envs: swap, 
 combination match, full cascade loop (detect / classify / activate / gravity / refill until stable),
 playability repair, timer/termination, legal-move mask, and the autoreset (generate_board) of every env whose
 episode ended.  Workload = BASELINE.json configs[1]: 10x10, 4 colours, cookie + v/h laser + bomb,
-num_moves=30, 65536 envs per GPU (weak scaling), uniform random actions.  Episodes are staggered
-(timer_0 = env % 30) so that every step resets 1/30 of the envs -- the steady state of a long run -- and any
---steps value measures the same per-step work.
+num_moves=30, 65536 envs per GPU (weak scaling), uniform random actions.  Episodes are synchronised, as they are
+for the reference (fixed-length episodes that all start at reset()): every 30th step ends all episodes and every
+env gets its next board in that step.  The default --steps 120 covers four whole episodes; --stagger env|pair
+spreads the episode phases instead (1/30 of the envs reset in every step).
 
 Prints ONE JSON line (rank 0).  `value` times tmg_step with inputs resident in HBM (CUDA events around each
 launch, L2 flushed between steps); `e2e` times the host-buffer call tmg_step_host (actions from pinned host
@@ -80,18 +81,23 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_port_throughput(num_envs, steps, threads):
+def cpu_port_throughput(threads, target_s=10.0):
     """The CPU statement of the same path (oracle/tmg_oracle.c, a literal C port of the reference's algorithm),
-    looped on the host cores over a bounded sample of the same workload.  Checker code used as a *baseline*."""
+    looped on the host cores over a bounded sample of the same workload (same shape, specials, num_moves, same-step
+    autoreset, uniform actions; ~target_s seconds of work).  Checker code used as a *baseline*, never as product."""
     from oracle.oracle import OracleVecEnv
+    num_envs = max(threads * 256, 2048)
     o = OracleVecEnv(num_envs, ROWS, COLS, COLOURS, NUM_MOVES, CL, CS, seed=SEED, autoreset="same_step", num_threads=threads)
     o.reset()
-    o.timer[:] = [e % NUM_MOVES for e in range(num_envs)]
-    o.rollout(3, 99, 0)  # warm-up
     t0 = time.perf_counter()
-    o.rollout(steps, 99, 3)
+    o.rollout(NUM_MOVES, 99, 0)                      # one whole episode: warm-up + calibration
+    cal = time.perf_counter() - t0
+    episodes = max(1, min(200, int(target_s / max(cal, 1e-3))))
+    steps = episodes * NUM_MOVES
+    t0 = time.perf_counter()
+    o.rollout(steps, 99, NUM_MOVES)
     dt = time.perf_counter() - t0
-    return num_envs * steps / dt, dt
+    return num_envs * steps / dt, dt, num_envs, steps
 
 
 def run_reference(args, rank):
@@ -101,21 +107,19 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = max(threads * 64, 1024)
-    per_call = 40
-    for _ in range(max(args.warmup, 1)):
-        cpu_port_throughput(n, 4, threads)
-    vals, t_tot = [], 0.0
-    for _ in range(max(1, min(args.steps, 8))):
-        v, dt = cpu_port_throughput(n, per_call, threads)
-        vals.append(v); t_tot += dt
-    v = statistics.median(vals)
+    # --steps / --warmup size the GPU arm; this arm times whole episodes of a bounded sample instead
+    vals, samples = [], []
+    for _ in range(2):
+        v, dt, n, steps = cpu_port_throughput(threads, target_s=8.0)
+        vals.append(v); samples.append((n, steps, dt))
+    v = max(vals)
+    n, per_call, _ = samples[vals.index(v)]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * ENVS_PER_GPU / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": workload_config(1),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{n} envs x {per_call} steps per timed call, {len(vals)} calls, median; "
+                             "sample": f"{n} envs x {per_call} steps (whole episodes) per timed call, best of {len(vals)} calls; "
                                        "oracle/tmg_oracle.c (C port of the Python reference) on all host threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -124,7 +128,7 @@ def run_reference(args, rank):
 
 def workload_config(n_gpus):
     return {"workload": "TileMatchEnv 10x10, 4 colours, specials=[vertical_laser,horizontal_laser,bomb,cookie], "
-                        "65536 envs per GPU, num_moves=30, uniform random actions, same-step autoreset, staggered episodes",
+                        "65536 envs per GPU, num_moves=30, uniform random actions, same-step autoreset, synchronised episodes",
             "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus, "num_moves": NUM_MOVES,
             "parallelism": f"env-index sharding x{n_gpus}, no step-path collective",
             "l2": "flushed between timed steps (256 MiB memset); per-GPU state 29 MB is L2-resident otherwise",
@@ -138,7 +142,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
-    ap.add_argument("--no-stagger", action="store_true")
+    ap.add_argument("--stagger", default="none", choices=["none", "env", "pair"],
+                    help="episode phases: none = synchronised (reference behaviour), env = timer0 = env %% num_moves")
+    ap.add_argument("--no-stagger", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--num-moves", type=int, default=NUM_MOVES, help="diagnostic: episode length (huge = no resets)")
@@ -168,8 +174,9 @@ def main():
     env = TileMatchVecEnv(n_local, ROWS, COLS, COLOURS, num_moves, CL, CS, seed=SEED, device=dev, autoreset="same_step",
                           env_id_offset=rank * n_local)
     env.reset()
-    if not args.no_stagger:
-        env.timer.copy_((torch.arange(n_local, device=dev) + rank * n_local) % num_moves)
+    if args.stagger != "none" and not args.no_stagger:
+        ids = torch.arange(n_local, device=dev) + rank * n_local
+        env.timer.copy_((ids // 2 if args.stagger == "pair" else ids) % num_moves)
         env.num_moves_left.copy_(num_moves - env.timer)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     n_act = 16
@@ -257,11 +264,11 @@ def main():
         }
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = max(threads * 64, 1024)
-            v, dt = cpu_port_throughput(n, 40, threads)
+            v, dt, n, steps = cpu_port_throughput(threads, target_s=10.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n} envs x 40 steps of the same workload ({dt:.1f} s), oracle/tmg_oracle.c "
-                                              "(C port of the Python reference) on all host threads"}
+                                    "sample": f"{n} envs x {steps} steps of the same workload ({dt:.1f} s), oracle/tmg_oracle.c "
+                                              "(C port of the Python reference; the Python original runs ~1e3 steps/s/core) "
+                                              "on all host threads"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

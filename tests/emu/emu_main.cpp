@@ -143,6 +143,7 @@ template <int L> static void launch(void (*fn)(), int n) {
 struct EmuEnv {
     Params p;
     int L;
+    int tag = 0;
     std::vector<char> mem;
 };
 
@@ -177,9 +178,9 @@ void* emu_create(const emu_config* c) {
     const size_t N = (size_t)p.N;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
-    size_t o[18] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
+    size_t o[19] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
                     take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4), take(N * 4), take(N * 4),
-                    take(N * 2 * p.P), take(N * p.A), take(N * 4)};
+                    take(N * 2 * p.P), take(N * p.A), take(N * 4), take(N * 4)};
     e->mem.assign(off + 256, 0);
     char* b = e->mem.data();
     b += (256 - ((uintptr_t)b & 255)) & 255;
@@ -190,6 +191,8 @@ void* emu_create(const emu_config* c) {
     p.status = (uint32_t*)(b + o[12]);
     p.episode = (int32_t*)(b + o[13]); p.pool_episode = (int32_t*)(b + o[14]);
     p.pool_board = (int8_t*)(b + o[15]); p.pool_mask = (uint8_t*)(b + o[16]); p.pool_status = (uint32_t*)(b + o[17]);
+    p.pool_req = (int32_t*)(b + o[18]);
+    for (size_t i = 0; i < N; ++i) p.pool_req[i] = -1;
     for (size_t i = 0; i < N; ++i) { p.timer[i] = -1; p.episode[i] = -1; p.pool_episode[i] = (int32_t)0x80808080; }
     return e;
 }
@@ -212,15 +215,15 @@ void emu_set_injected_draws(void* h, const uint8_t* d, int64_t len) { ((EmuEnv*)
 
 void emu_reset(void* h, const uint8_t* reset_mask, const int8_t* init_boards) {
     EmuEnv* e = (EmuEnv*)h;
-    g_params = e->p; g_params.reset_mask = reset_mask; g_params.init_boards = init_boards;
+    g_params = e->p; g_params.reset_mask = reset_mask; g_params.init_boards = init_boards; g_params.pool_tag = e->tag;
     DISPATCH(e_reset)
-    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; DISPATCH(e_pregen) }
+    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; g_params.pool_tag = e->tag++; DISPATCH(e_pregen) }
 }
 void emu_step(void* h, const int32_t* actions) {
     EmuEnv* e = (EmuEnv*)h;
-    g_params = e->p; g_params.actions = actions;
+    g_params = e->p; g_params.actions = actions; g_params.pool_tag = e->tag;
     DISPATCH(e_step)
-    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; DISPATCH(e_pregen) }
+    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; g_params.pool_tag = e->tag++; DISPATCH(e_pregen) }
 }
 void emu_legal_mask(void* h) {
     EmuEnv* e = (EmuEnv*)h;

@@ -21,8 +21,9 @@ struct tmg_env {
     void* base;     // one allocation backs every buffer
     size_t bytes;
     // board pool: k_pregen runs on a side stream so that generate_board stays off the step path
-    cudaStream_t side;
-    static constexpr int RING = 16;
+    static constexpr int SIDE = 4;    // independent refill launches overlap each other and the steps
+    static constexpr int RING = 32;   // multiple of SIDE: an event slot always belongs to the same side stream
+    cudaStream_t side[SIDE];
     cudaEvent_t ev_step, ev_pregen[RING];
     long long pregen_count;   // number of k_pregen launches so far
     bool pregen;              // pool in use (philox refill, not disabled by flag)
@@ -75,25 +76,35 @@ template <int L> int grid_for(int n) { return (n + Cfg<L>::GPB - 1) / Cfg<L>::GP
 
 }  // namespace
 
-// `st` waits until every k_pregen launched so far has finished (used by the rare calls that rewrite env state)
-static bool join_pregen(tmg_env* e, cudaStream_t st) {
-    if (!e->pregen || e->pregen_count == 0) return true;
-    return cudaStreamWaitEvent(st, e->ev_pregen[(e->pregen_count - 1) % tmg_env::RING], 0) == cudaSuccess;
+// `st` waits until every k_pregen launch with tag <= upto has finished (one wait per side stream)
+static bool wait_pregen(tmg_env* e, cudaStream_t st, long long upto) {
+    if (!e->pregen) return true;
+    for (int s = 0; s < tmg_env::SIDE; ++s) {
+        if (upto < s) continue;
+        const long long j = upto - ((upto - s) % tmg_env::SIDE);   // latest tag <= upto on side stream s
+        // (if that slot was reused by a later launch of the same stream the wait is only stronger)
+        if (cudaStreamWaitEvent(st, e->ev_pregen[j % tmg_env::RING], 0) != cudaSuccess) return false;
+    }
+    return true;
 }
-// after a kernel on `st` that may have consumed pool entries: refill them on the side stream
+static bool join_pregen(tmg_env* e, cudaStream_t st) { return wait_pregen(e, st, e->pregen_count - 1); }
+// after a kernel on `st` that tagged pool requests with e->pregen_count: serve them on a side stream
 static int launch_pregen(tmg_env* e, cudaStream_t st) {
     if (!e->pregen) return TMG_OK;
+    const long long tag = e->pregen_count;
+    cudaStream_t side = e->side[tag % tmg_env::SIDE];
     if (cudaEventRecord(e->ev_step, st) != cudaSuccess) return TMG_ERR_CUDA;
-    if (cudaStreamWaitEvent(e->side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
-    const Params p = e->p;
+    if (cudaStreamWaitEvent(side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
+    Params p = e->p;
+    p.pool_tag = (int)(tag & 0x7fffffff);
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
-        k_pregen<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), e->side>>>(p);
+        k_pregen<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), side>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
-    if (cudaEventRecord(e->ev_pregen[e->pregen_count % tmg_env::RING], e->side) != cudaSuccess) return TMG_ERR_CUDA;
+    if (cudaEventRecord(e->ev_pregen[tag % tmg_env::RING], side) != cudaSuccess) return TMG_ERR_CUDA;
     ++e->pregen_count;
     return TMG_OK;
 }
@@ -188,7 +199,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_mask = take((size_t)N * p.A), o_left = take((size_t)N * 4), o_stat = take((size_t)N * 4),
                  o_actions = take((size_t)N * 4), o_ep = take((size_t)N * 4), o_pool_ep = take((size_t)N * 4),
                  o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
-                 o_pool_status = take((size_t)N * 4);
+                 o_pool_status = take((size_t)N * 4), o_pool_req = take((size_t)N * 4);
     e->bytes = off;
     if (cudaMalloc(&e->base, e->bytes) != cudaSuccess) { cudaGetLastError(); delete e; return TMG_ERR_OOM; }
     if (cudaMemset(e->base, 0, e->bytes) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
@@ -212,13 +223,15 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.pool_board = reinterpret_cast<int8_t*>(b + o_pool_board);
     p.pool_mask = reinterpret_cast<uint8_t*>(b + o_pool_mask);
     p.pool_status = reinterpret_cast<uint32_t*>(b + o_pool_status);
+    p.pool_req = reinterpret_cast<int32_t*>(b + o_pool_req);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
-    e->side = nullptr;
+    for (int i = 0; i < tmg_env::SIDE; ++i) e->side[i] = nullptr;
     bool ok = cudaMemset(p.episode, 0xff, (size_t)N * 4) == cudaSuccess &&       // -1: no board generated yet
-              cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess;    // never equal to a real episode
+              cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess &&  // never equal to a real episode
+              cudaMemset(p.pool_req, 0xff, (size_t)N * 4) == cudaSuccess;
     if (e->pregen) {
-        ok = ok && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < tmg_env::SIDE; ++i) ok = ok && cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < tmg_env::RING; ++i) ok = ok && cudaEventCreateWithFlags(&e->ev_pregen[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -234,10 +247,10 @@ int tmg_destroy(tmg_env* e) {
     if (!e) return TMG_ERR_INVALID_ARG;
     cudaSetDevice(e->cfg.device);
     if (e->pregen) {
-        cudaStreamSynchronize(e->side);
+        for (int i = 0; i < tmg_env::SIDE; ++i) cudaStreamSynchronize(e->side[i]);
         cudaEventDestroy(e->ev_step);
         for (int i = 0; i < tmg_env::RING; ++i) cudaEventDestroy(e->ev_pregen[i]);
-        cudaStreamDestroy(e->side);
+        for (int i = 0; i < tmg_env::SIDE; ++i) cudaStreamDestroy(e->side[i]);
     }
     cudaFree(e->base);
     delete e;
@@ -269,6 +282,7 @@ int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boar
     p.reset_mask = reset_mask_dev;
     p.init_boards = init_boards_dev;
     p.init_vecw = init_boards_dev ? ptr_vec_width(init_boards_dev, p.board_vecw) : p.board_vecw;
+    p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!join_pregen(e, st)) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
@@ -287,13 +301,12 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
     Params p = e->p;
     p.actions = actions_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
     if (e->pregen) {
-        // An env consumes its pool entry at most once per episode, so the refill launched W steps ago (W <= num_moves)
-        // is the latest one this step can depend on; everything newer keeps running beside the step kernels.
-        const long long W = p.num_moves < 8 ? p.num_moves : 8;
-        if (e->pregen_count >= W &&
-            cudaStreamWaitEvent(st, e->ev_pregen[(e->pregen_count - W) % tmg_env::RING], 0) != cudaSuccess)
-            return TMG_ERR_CUDA;
+        // An env consumes its pool entry at most once per episode, so only refills tagged num_moves or more launches
+        // ago can be needed by this step; everything newer keeps running beside the step kernels.
+        const long long W = p.num_moves < 24 ? p.num_moves : 24;   // < RING - SIDE so the event slots are still live
+        if (!wait_pregen(e, st, e->pregen_count - W)) return TMG_ERR_CUDA;
     }
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;

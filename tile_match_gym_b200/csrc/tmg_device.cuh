@@ -75,6 +75,8 @@ struct Params {
     uint8_t* pool_mask;      // [N][A]       its legal-move mask
     int32_t* pool_episode;   // [N]          which episode the pool entry belongs to (-1 = none)
     uint32_t* pool_status;   // [N]          status bits raised while generating it (merged when it is consumed)
+    int32_t* pool_req;       // [N]          tag of the k_pregen launch that must refill this env's entry
+    int pool_tag;            // tag handed out by this launch (k_step / k_reset) or served by it (k_pregen)
     // per-call inputs
     const int32_t* actions;
     const uint8_t* reset_mask;
@@ -1209,7 +1211,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         b.begin_generate((uint32_t)ep);
         b.playability(false, true, effv, effh);
         b.end_generate();
-        if (gc.lane == 0) p.episode[gc.env] = ep;
+        if (gc.lane == 0) { p.episode[gc.env] = ep; p.pool_req[gc.env] = p.pool_tag; }
     }
     b.store_board();
     b.store_cursors();
@@ -1311,7 +1313,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); }
         }
     }
-    if (regenerate && lane == 0) p.episode[env] = next_ep;
+    if (regenerate && lane == 0) { p.episode[env] = next_ep; p.pool_req[env] = p.pool_tag; }
     merge_status(b, p);
     write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled);
     if (p.prof && lane == 0) {
@@ -1327,6 +1329,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_pregen(const Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
+    if (p.pool_req[gc.env] != p.pool_tag) return;   // each launch serves exactly the requests tagged for it
     const int ep = p.episode[gc.env] + 1;
     if (p.pool_episode[gc.env] == ep) return;
     Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
