@@ -262,7 +262,7 @@ def main():
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "drain_ms": drain_ms, "wall_s": t_wall, "status_flags_set": status_bad,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only
             threads = os.cpu_count() or 1
             v, dt, n, steps = cpu_port_throughput(threads, target_s=10.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -202,8 +202,9 @@ int tmg_step_host(tmg_env *env, const tmg_host_io *io, void *stream);
 #define TMG_OP_COUNT_LINES 10   /* len(get_colour_lines()) -> reward                          board.py:149-215 */
 int tmg_debug_op(tmg_env *env, int32_t op, const int32_t *args_dev, void *stream);
 
-/* Diagnostics: when set, every tmg_step writes per env {SM cycles spent, cycles inside leader-lane serial sections,
- * cascade rounds, redraw iterations} to prof_dev (device uint32 [N][4]); NULL switches it off. */
+/* Diagnostics: when set, every tmg_step writes per env {SM cycles spent, cycles in the general (non-fast) round path,
+ * cascade rounds, redraw iterations} and ADDS the general path's cycles split into {scan, line table, classification,
+ * resolution} to prof_dev (device uint32 [N][8], zero it before the step); NULL switches it off. */
 int tmg_set_profile_buffer(tmg_env *env, uint32_t *prof_dev);
 
 #ifdef __cplusplus

@@ -23,12 +23,13 @@ if a.stagger == "env":
     env.timer.copy_(torch.arange(a.envs, device="cuda") % a.num_moves)
 elif a.stagger == "pair":
     env.timer.copy_((torch.arange(a.envs, device="cuda") // 2) % a.num_moves)
-prof = torch.zeros((a.envs, 4), dtype=torch.int32, device="cuda")
+prof = torch.zeros((a.envs, 8), dtype=torch.int32, device="cuda")
 env._lib.tmg_set_profile_buffer(env._h, C.c_void_p(prof.data_ptr()))
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 for t in range(a.steps):
     act = torch.randint(0, env.num_actions, (a.envs,), device="cuda", dtype=torch.int32, generator=g)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof.zero_()
     e0.record(); env.step(act); e1.record(); torch.cuda.synchronize()
     if t >= a.steps - 3:
         pr = prof.cpu().numpy().astype("int64")
@@ -38,8 +39,11 @@ for t in range(a.steps):
         print(f"step {t}: kernel {e0.elapsed_time(e1)*1e3:.0f} us; env cycles: mean {cyc.mean():.0f} p50 {np.percentile(cyc,50):.0f} "
               f"p99 {np.percentile(cyc,99):.0f} p99.9 {np.percentile(cyc,99.9):.0f} max {cyc.max()} "
               f"(= {cyc.max()/1.965e3:.0f} us at 1.965 GHz); sum {cyc.sum()/1e6:.0f} Mcyc")
+        act = env.num_specials_activated.cpu().numpy(); new = env.num_new_specials.cpu().numpy(); rew = env.reward.cpu().numpy()
         for i in order:
-            print(f"   env {i}: cycles {cyc[i]} serial {ser[i]} rounds {rounds[i]} redraws {iters[i]}")
+            print(f"   env {i}: cycles {cyc[i]} slow-path cycles {ser[i]} rounds {rounds[i]} redraws {iters[i]} "
+                  f"activated {act[i]} new_specials {new[i]} reward {rew[i]} | general path: scan {pr[i,4]} table {pr[i,5]} "
+                  f"classify {pr[i,6]} resolve {pr[i,7]}")
         eff = rounds > 0
         if eff.any():
             print(f"   effective moves {eff.sum()}: cycles/round {cyc[eff & (iters == 0)].sum() / max(1, rounds[eff & (iters == 0)].sum()):.0f}, "

@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libtmg_b200.so")
+LIB_PATH = os.environ.get("TMG_B200_LIB", os.path.join(_HERE, "libtmg_b200.so"))  # override: A/B builds only
 SRC = os.path.join(_HERE, "csrc", "tmg_b200.cu")
 DEVICE_HDR = os.path.join(_HERE, "csrc", "tmg_device.cuh")
 ABI_HDR = os.path.join(ROOT, "include", "tmg_b200.h")

@@ -83,7 +83,8 @@ struct Params {
     const int8_t* init_boards;
     const int32_t* dbg_args;
     int dbg_op;
-    uint32_t* prof;  // optional [N][4]: cycles total, cycles in leader-serial sections, cascade rounds, redraw iterations
+    uint32_t* prof;  // optional [N][8]: cycles total, cycles in the general path, cascade rounds, redraw iterations,
+                     // then general-path cycles split into scan / line table / classification / resolution (zero before each step)
 };
 
 template <int L> struct Cfg {
@@ -228,6 +229,16 @@ __device__ __noinline__ void shuffle_serial(int8_t* col, int8_t* typ, int P, uin
 // ======================================================================================================
 // One board owned by a group of L lanes
 // ======================================================================================================
+// The rare, large parts of a cascade round run out of line on a private Board view, so that the common round
+// (scan, fast path, gravity, refill) stays small enough for the instruction caches.
+struct SlowOut { int n, n_new, n_act; uint32_t status; };
+template <int L, int RT, int CT>
+__device__ __noinline__ SlowOut slow_round(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env,
+                                           int n_new, int n_act);
+template <int L, int RT, int CT>
+__device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift,
+                                                 int env, int i1, int i2);
+
 // RT/CT > 0 fix the board shape at compile time (full unrolling, immediate shared-memory offsets); 0 = runtime shape.
 template <int L, int RT = 0, int CT = 0> struct Board {
     typedef Cfg<L> CF;
@@ -403,10 +414,10 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // ---- line detection (ref :149-215) ---------------------------------------------------------------------
     // Per-lane row bitboards of column c: E bit r: colour(r,c)==colour(r,c+1); D bit r: colour(r,c)==colour(r-1,c);
     // T bit r: type(r,c) > 0.  One pass over the column finds every anchored line of the board at once.
-    struct Bits { unsigned E, D, T; };
+    struct Bits { unsigned E, D, T, S; };  // S bit r: type(r,c) not in {0,1} (a special tile)
     __device__ __forceinline__ Bits column_bits(bool all_normal) const {
         Bits b;
-        b.E = b.D = b.T = 0u;
+        b.E = b.D = b.T = b.S = 0u;
         if (lane < C) {
             int prev = -3;
             const bool has_right = lane + 1 < C;
@@ -417,7 +428,11 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                 const int xr = has_right ? (int)col[i + 1] : -2;
                 b.E |= (unsigned)(x == xr) << r;
                 b.D |= (unsigned)(x == prev) << r;
-                if (!all_normal) b.T |= (unsigned)(typ[i] > 0) << r;
+                if (!all_normal) {
+                    const int t = typ[i];
+                    b.T |= (unsigned)(t > 0) << r;
+                    b.S |= (unsigned)not01(t) << r;
+                }
                 prev = x;
             }
             if (all_normal) b.T = rows_mask();
@@ -484,6 +499,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             const int slot = before;
             if (slot < CF::ML) {
                 const int len = rs - sc.vtop + 1;
+#pragma unroll 1
                 for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)((sc.vtop + k) * C + lane);
                 s.line_len[slot] = (uint8_t)len;
                 s.line_colour[slot] = (uint8_t)col[rs * C + lane];
@@ -494,6 +510,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             const int slot = before + (sc.has_v ? 1 : 0);
             if (slot < CF::ML) {
                 const int run = __ffs((int)~(sc.m >> lane)) - 1;
+#pragma unroll 1
                 for (int k = 0; k <= run; ++k) s.line_cells[slot][k] = (uint16_t)(rs * C + lane + k);
                 s.line_len[slot] = (uint8_t)(run + 1);
                 s.line_colour[slot] = (uint8_t)col[rs * C + lane];
@@ -503,6 +520,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         // phase 2 (ref :198-214): horizontal segments through the cells of the vertical lines, cut at phase-1 cells
         if (sc.mv) {
             const int rmin_ = rmin(sc.has_v ? sc.vtop : 1 << 20);
+#pragma unroll 1
             for (int r = rmin_; r <= rs; ++r) {
                 const unsigned m = ballot((sc.bits.E >> r) & 1u);
                 const unsigned T = ballot((sc.bits.T >> r) & 1u);
@@ -524,6 +542,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                     const int slot = n + __popc(segm & lt);
                     if (slot < CF::ML) {
                         const int len = 1 + left + right;
+#pragma unroll 1
                         for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)(r * C + lane - left + k);
                         s.line_len[slot] = (uint8_t)len;
                         s.line_colour[slot] = (uint8_t)col[r * C + lane];
@@ -554,7 +573,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     __device__ __forceinline__ int count_nonzero_colours() {
         int n = 0;
         if (lane < C) {
-#pragma unroll
+#pragma unroll 1
             for (int r = 0; r < (RT ? RT : R); ++r) n += (col[r * C + lane] != 0);
         }
         return radd(n);
@@ -566,10 +585,11 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // entry of activate_special (ref :473-499 + the set-up of the cookie branch :530-544); pushes a frame.
     // All lanes, uniform arguments.  Board writes of other lanes must be visible (callers sync before).
     __device__ void enter_activation(int cell, int t, bool counted, int& sp) {
-        int nz = count_nonzero_colours();
-        if (nz == 0) return;                                   // ref :488-489
-        if (t == 0 || t == 1) { status |= ST_INTERNAL; return; }  // ref :491-492 raises
         const int own_nz = col[cell] != 0;
+        // ref :488-489 "all colours zero": impossible when the target itself is coloured, so only colourless targets count
+        int nz = own_nz ? 1 : count_nonzero_colours();
+        if (nz == 0) return;
+        if (t == 0 || t == 1) { status |= ST_INTERNAL; return; }  // ref :491-492 raises
         sync();                                                // every lane has read the cell
         if (lane == 0) { col[cell] = 0; typ[cell] = 0; }       // ref :496
         if (counted) ++n_act;                                  // ref :498-499
@@ -579,22 +599,25 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         else if (t == 4) kind = 2;
         else if (t == -1) {
             kind = 3;
+            if (own_nz) nz = count_nonzero_colours();          // (a coloured cookie only exists after a shuffle + redraw)
             nz -= own_nz;
             if (nz == 0) { sync(); return; }                   // ref :532-534
             sync();
-            int best = 0;                                      // ref :536-537: most common colour, lowest on ties
+            int best = 0, seen = 0;                            // ref :536-537: most common colour, lowest on ties
+#pragma unroll 1
             for (int k = 1; k < 32; ++k) {
-                if (k > K && best > 0 && k > 8) break;         // colours above K only exist on hand-made boards
+                if (k > K && seen >= nz) break;                // colours above K only exist on hand-made boards
                 int c = 0;
                 if (lane < C) {
-#pragma unroll
-                    for (int r = 0; r < (RT ? RT : R); ++r) c += (col[r * C + lane] == k);
+#pragma unroll 1
+                    for (int r = 0; r < R; ++r) c += (col[r * C + lane] == k);
                 }
                 c = radd(c);
+                seen += c;
                 if (c > best) { best = c; mc = k; }
             }
             if (lane < C) {                                    // ref :540-544: delete its normal tiles
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < (RT ? RT : R); ++r) {
                     const int i = r * C + lane;
                     if (col[i] == mc && typ[i] == 1) { col[i] = 0; typ[i] = 0; }
@@ -608,6 +631,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     }
     // first index i in [cur, n) (lanes test i = base + lane) for which pred(i) holds, else n
     template <typename F> __device__ __forceinline__ int first_in_order(int cur, int n, F&& pred) {
+#pragma unroll 1
         for (int base = cur; base < n; base += L) {
             const int i = base + lane;
             const unsigned m = ballot(i < n && pred(i));
@@ -616,6 +640,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         return n;
     }
     template <typename F> __device__ __forceinline__ void delete_in_order(int cur, int end, F&& cell_of) {
+#pragma unroll 1
         for (int i = cur + lane; i < end; i += L) {
             const int q = cell_of(i);
             col[q] = 0;
@@ -626,6 +651,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     __device__ void activate(int cell0, int t0, bool counted) {
         int sp = 0;
         enter_activation(cell0, t0, counted, sp);
+#pragma unroll 1
         while (sp > 0) {
             sync();
             const uint32_t f = s.stack[sp - 1];
@@ -654,6 +680,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             } else {                                           // cookie: specials of its colour, row-major (ref :547-554)
                 int cand = 1 << 20;
                 if (lane < C)
+#pragma unroll 1
                     for (int r = cur / C; r < R; ++r) {
                         const int i = r * C + lane;
                         if (i >= cur && col[i] == mc && typ[i] > 1) { cand = i; break; }
@@ -673,23 +700,28 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // get_special_creation_pos (ref :429-458) on s.match[0..n); leader lane
     __device__ __forceinline__ int creation_pos(int n, int ntaken, bool straight) {
         auto is_taken = [&](int cell) {
+#pragma unroll 1
             for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
             return false;
         };
         int nv = 0;
+#pragma unroll 1
         for (int k = 0; k < n; ++k) nv += !is_taken(s.match[k]);
         if (nv == 0) return -1;                                 // reference: IndexError
         if (!straight) {                                        // ref :441-450
             int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
+#pragma unroll 1
             for (int k = 0; k < n; ++k) {                       // max(xs, key=xs.count): first element with the top count
                 const int rr = s.match[k] / C, cc = s.match[k] % C;
                 int nr = 0, nc = 0;
+#pragma unroll 1
                 for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
                 if (nr > best_rc) { best_rc = nr; best_r = rr; }
                 if (nc > best_cc) { best_cc = nc; best_c = cc; }
             }
             const int corner = best_r * C + best_c;
             int best = -1, bestd = 0;
+#pragma unroll 1
             for (int k = 0; k < n; ++k) {
                 const int cell = s.match[k];
                 if (is_taken(cell)) continue;
@@ -702,6 +734,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         // straight: the match is already sorted by (row, col); pick the middle of the valid cells (ref :453-458)
         const int want = (nv % 2 == 0) ? nv / 2 - 1 : nv / 2;
         int seen = 0;
+#pragma unroll 1
         for (int k = 0; k < n; ++k) {
             if (is_taken(s.match[k])) continue;
             if (seen == want) return s.match[k];
@@ -715,11 +748,14 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // Returns nm | ncq << 16 | flags << 24 (flag 1: table overflow, flag 2: no valid creation cell).
     __device__ __forceinline__ uint32_t classify_lines(int n) {
         // ref :282: stable sort by the first cell's row == sort by key (keys are unique)
+#pragma unroll 1
         for (int i = 0; i < n; ++i) s.order[i] = (uint8_t)i;
+#pragma unroll 1
         for (int i = 1; i < n; ++i) {
             const uint8_t v = s.order[i];
             const uint32_t kv = s.line_key[v];
             int j = i - 1;
+#pragma unroll 1
             while (j >= 0 && s.line_key[s.order[j]] > kv) { s.order[j + 1] = s.order[j]; --j; }
             s.order[j + 1] = v;
         }
@@ -728,6 +764,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         uint32_t flags = 0u;
         const bool sp_cookie = p.specials & SP_COOKIE, sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER,
                    sp_bomb = p.specials & SP_BOMB;
+#pragma unroll 1
         while (qh < qn) {
             const int li = s.order[qh++];                    // ref :285 pop(0)
             const int len = s.line_len[li];
@@ -735,11 +772,13 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             int mlen = 0, name = NAME_NORMAL, colour = s.line_colour[li];
             bool have = false;
             if (len >= 5 && sp_cookie) {                     // ref :287-292
+#pragma unroll 1
                 for (int k = 0; k < 5; ++k) s.match[mlen++] = cells[k];
                 name = NAME_COOKIE; colour = 0; have = true;
                 if (len - 5 > 2) {
                     if (nslots < CF::ML && qn < CF::ML) {
                         const int ns = nslots++;
+#pragma unroll 1
                         for (int k = 5; k < len; ++k) s.line_cells[ns][k - 5] = cells[k];
                         s.line_len[ns] = (uint8_t)(len - 5);
                         s.line_colour[ns] = s.line_colour[li];
@@ -747,6 +786,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                     } else flags |= 1u;
                 }
             } else if (len == 4) {                           // ref :294-302
+#pragma unroll 1
                 for (int k = 0; k < 4; ++k) s.match[mlen++] = cells[k];
                 const bool horizontal = (cells[0] / C) == (cells[1] / C);
                 name = (horizontal && sp_h) ? NAME_HLASER : (sp_v ? NAME_VLASER : NAME_NORMAL);
@@ -754,9 +794,12 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             } else {
                 int hit = -1, shared = -1;
                 if (sp_bomb) {                               // ref :304-308: first queued line sharing a cell
+#pragma unroll 1
                     for (int q = qh; q < qn && hit < 0; ++q) {
                         const int lj = s.order[q];
+#pragma unroll 1
                         for (int k = 0; k < len && hit < 0; ++k)
+#pragma unroll 1
                             for (int u = 0; u < s.line_len[lj]; ++u)
                                 if (s.line_cells[lj][u] == cells[k]) { hit = q; shared = cells[k]; break; }
                     }
@@ -766,12 +809,15 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                     const int llen = s.line_len[lj];
                     uint16_t* lc = s.line_cells[lj];
                     const int sr = shared / C, scc = shared % C;
+#pragma unroll 1
                     for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
                     // first three of the stable sort of l by Manhattan distance (ref :310)
                     int picked[3] = {-1, -1, -1};
                     const int take = llen < 3 ? llen : 3;
+#pragma unroll 1
                     for (int a = 0; a < take; ++a) {
                         int bi = -1, bd = 0;
+#pragma unroll 1
                         for (int u = 0; u < llen; ++u) {
                             if (u == picked[0] || u == picked[1]) continue;
                             const int d = abs(lc[u] / C - sr) + abs(lc[u] % C - scc);
@@ -779,20 +825,24 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                         }
                         picked[a] = bi;
                         bool in_line = false;
+#pragma unroll 1
                         for (int k = 0; k < len; ++k) in_line |= (cells[k] == lc[bi]);
                         if (!in_line) s.match[mlen++] = lc[bi];  // ref :312
                     }
                     name = NAME_BOMB; have = true;
                     if (llen < 6) {                          // ref :315-316 (lines are distinct by value)
+#pragma unroll 1
                         for (int q = hit; q + 1 < qn; ++q) s.order[q] = s.order[q + 1];
                         --qn;
                     } else {                                 // ref :317-319: drop the three cells, keep the order
                         int w = 0;
+#pragma unroll 1
                         for (int u = 0; u < llen; ++u)
                             if (u != picked[0] && u != picked[1] && u != picked[2]) lc[w++] = lc[u];
                         s.line_len[lj] = (uint8_t)w;
                     }
                 } else if (len >= 3) {                       // ref :322-325
+#pragma unroll 1
                     for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
                     have = true;
                 }
@@ -809,6 +859,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                     ++ncq;
                 }
             }
+#pragma unroll 1
             for (int k = 0; k < mlen; ++k) {                 // cells in resolve order (ref :421-423, :467)
                 if (nm < MCAP) out[nm++] = s.match[k];
                 else flags |= 1u;
@@ -825,6 +876,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         if (flags & 2u) status |= ST_INTERNAL;
         const uint16_t* ml = mlist();
         int pos = 0;
+#pragma unroll 1
         while (pos < nm) {                                   // ref :421-423 -> resolve_colour_match :460-471
             auto cell_of = [&](int i) { return (int)ml[i]; };
             const int first = first_in_order(pos, nm, [&](int i) { return not01(typ[cell_of(i)]); });
@@ -837,6 +889,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             pos = first + 1;
         }
         sync();
+#pragma unroll 1
         for (int i = lane; i < ncq; i += L) {                // ref :426-427 -> create_special :572-597
             if (s.cq_pos[i] == 0xffff) continue;
             col[s.cq_pos[i]] = (int8_t)s.cq_colour[i];
@@ -845,111 +898,181 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         n_new += ncq;
     }
 
-    // one cascade round without gravity/refill (ref :369-373); returns the number of lines found
-    __device__ int resolve_round() {
+    // Fast path of a cascade round (most rounds): the lines anchored on row r* are all 3 or 4 long, pairwise disjoint,
+    // contain no special tile and have no crossing segments.  Then process_colour_lines yields one normal / laser
+    // match per line (ref :294-302,322-325), nothing is activated, deletions commute, and the creation cell of a
+    // 4-line is its second cell (ref :453-456).  Returns the number of lines, or 0 if the general path must run.
+    __device__ __forceinline__ int fast_round(const Scan& sc) {
+        const Bits& b = sc.bits;
+        const int rs = sc.rstar;
+        const bool sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER;
+        const unsigned El = from_left(b.E, 1);               // bit r: my left neighbour has my colour
+        if (sc.mv == 0u) {                                   // horizontal lines only
+            const bool mine = (sc.hcells >> lane) & 1u;
+            const bool start = (sc.hs >> lane) & 1u;
+            const int len = start ? __ffs((int)~(sc.m >> lane)) : 0;          // run + 1
+            const unsigned long4 = ballot(start && len == 4);
+            if (ballot((mine && ((b.S >> rs) & 1u)) || len > 4)) return 0;
+            const int laser = sp_h ? 3 : (sp_v ? 2 : 0);                      // ref :297-302
+            const unsigned create = laser ? (long4 << 1) : 0u;               // second cell of each 4-line
+            if (mine) {
+                const int i = rs * C + lane;
+                if ((create >> lane) & 1u) typ[i] = (int8_t)laser;           // keeps the line's colour (ref :596-597)
+                else { col[i] = 0; typ[i] = 0; }
+            }
+            n_new += __popc(create);
+            return __popc(sc.hs);
+        }
+        if (sc.hs == 0u) {                                   // vertical lines only
+            const int len = sc.has_v ? rs - sc.vtop + 1 : 0;
+            const unsigned vrows = sc.has_v ? ((2u << rs) - 1u) & ~((1u << sc.vtop) - 1u) : 0u;
+            // a cell of the line with an equal horizontal neighbour could start a phase-2 segment (ref :198-214)
+            if (ballot((vrows & (b.S | b.E | El)) != 0u || len > 4)) return 0;
+            const bool make = sc.has_v && len == 4 && sp_v;                   // vertical 4-line -> vertical laser or normal
+            if (sc.has_v) {
+                for (int r = sc.vtop; r <= rs; ++r) {
+                    const int i = r * C + lane;
+                    if (make && r == sc.vtop + 1) typ[i] = 2;
+                    else { col[i] = 0; typ[i] = 0; }
+                }
+            }
+            n_new += __popc(ballot(make));
+            return __popc(sc.mv);
+        }
+        return 0;
+    }
+
+    // general path of a cascade round: line table, classification, resolution with activations
+    __device__ __forceinline__ int general_round() {
         sync();
+        const long long t0 = p.prof ? clock64() : 0;
         const Scan sc = scan_lines(R - 1, false);
         if (sc.rstar < 0) return 0;
+        const long long t1 = p.prof ? clock64() : 0;
         const int n = build_line_table(sc);
-        ++prof_rounds;
-        const long long t0 = p.prof ? clock64() : 0;
+        const long long t2 = p.prof ? clock64() : 0;
         uint32_t packed = 0u;
         if (lane == 0) packed = classify_lines(n);
         packed = (uint32_t)shfl((int)packed, 0);
         sync();
+        const long long t3 = p.prof ? clock64() : 0;
         resolve_matches(packed);
-        if (p.prof) prof_serial += (uint32_t)(clock64() - t0);
+        sync();
+        if (p.prof && lane == 0) {   // diagnostics: cycles per phase of the general path, accumulated per env
+            const long long t4 = clock64();
+            atomicAdd(&p.prof[env * 8 + 4], (uint32_t)(t1 - t0));
+            atomicAdd(&p.prof[env * 8 + 5], (uint32_t)(t2 - t1));
+            atomicAdd(&p.prof[env * 8 + 6], (uint32_t)(t3 - t2));
+            atomicAdd(&p.prof[env * 8 + 7], (uint32_t)(t4 - t3));
+        }
+        return n;
+    }
+
+    // one cascade round without gravity/refill (ref :369-373); returns the number of lines found
+    __device__ __forceinline__ int resolve_round() {
+        sync();
+        const Scan sc = scan_lines(R - 1, false);
+        if (sc.rstar < 0) return 0;
+        ++prof_rounds;
+        int n = fast_round(sc);
+        if (n == 0) {
+            const long long t0 = p.prof ? clock64() : 0;
+            const SlowOut o = slow_round<L, RT, CT>(&s, &p, lane, gmask, gshift, env, n_new, n_act);
+            n = o.n; n_new = o.n_new; n_act = o.n_act; status |= o.status;
+            if (p.prof) prof_serial += (uint32_t)(clock64() - t0);
+        }
         sync();
         return n;
     }
 
-    // activate every cell selected by `pred`, in row-major order, re-testing live cells (ref :721-726)
-    template <typename F> __device__ __forceinline__ void activate_row_major(F&& pred) {
-        int cur = 0;
-        for (;;) {
-            sync();
-            int cand = 1 << 20;
-            if (lane < C)
-                for (int r = cur / C; r < R; ++r) {
-                    const int i = r * C + lane;
-                    if (i >= cur && pred(i)) { cand = i; break; }
-                }
-            cand = rmin(cand);
-            if (cand >= (1 << 20)) break;
-            const int t = typ[cand];
-            sync();
-            activate(cand, t, false);
-            cur = cand + 1;
-        }
-    }
-    __device__ __forceinline__ void delete_two(int i1, int i2) {
-        sync();
-        if (lane == 0) { col[i1] = 0; typ[i1] = 0; col[i2] = 0; typ[i2] = 0; }
-        sync();
-    }
-
-    // combination_match (ref :600-719); all lanes, uniform control flow
-    __device__ void combination(int i1, int i2) {
+    // combination_match (ref :600-719); all lanes, uniform control flow.  Every branch reduces to a sequence of
+    // top-level activate_special calls (is_combination_match=True, i.e. not counted), produced by one driver loop so
+    // that the activation machinery is instantiated once.
+    __device__ __forceinline__ void combination(int i1, int i2) {
         n_act += 2;                                          // ref :609
         sync();
         const int t1 = typ[i1], k1 = col[i1], t2 = typ[i2], k2 = col[i2];
         const int r1 = i1 / C, c1 = i1 % C, r2 = i2 / C, c2 = i2 % C;
+        const int r = min(r1, r2), c = min(c1, c2);
         sync();
+        enum { NONE, LIST2, CROSS, ROWMAJOR, WINDOW };
+        int mode = NONE, kk = 0;
+        bool strict = false;                                 // ROWMAJOR: type > 1 (cookie+normal) vs type not in {0,1}
+        int min_r = 0, max_r = 0, min_c = 0, max_c = 0;
         if (t1 == -1 && t2 == -1) {                          // ref :615-616
+#pragma unroll 1
             for (int i = lane; i < P; i += L) { col[i] = 0; typ[i] = 0; }
         } else if ((t1 == -1 && t2 == 1) || (t1 == 1 && t2 == -1)) {  // ref :619-641
             const int ck = (t1 == -1) ? i1 : i2;
-            const int kk = (t1 == -1) ? k2 : k1;
+            kk = (t1 == -1) ? k2 : k1;
             if (lane == 0) { col[ck] = 0; typ[ck] = 0; }     // ref :626,628
             sync();
+#pragma unroll 1
             for (int i = lane; i < P; i += L) if (col[i] == kk && typ[i] == 1) { col[i] = 0; typ[i] = 0; }  // ref :631-635
             // snapshot mask colour==kk & type>1, visited row-major; cells can only disappear meanwhile (ref :638-640)
-            activate_row_major([&](int i) { return col[i] == kk && typ[i] > 1; });
+            mode = ROWMAJOR; strict = true;
             n_act -= 1;                                      // ref :641
         } else if ((t1 == -1 && t2 >= 2) || (t1 >= 2 && t2 == -1)) {  // ref :644-660
             const int ck = (t1 == -1) ? i1 : i2;
-            const int kk = (t1 == -1) ? k2 : k1;
+            kk = (t1 == -1) ? k2 : k1;
             const int tt = (t1 == -1) ? t2 : t1;
             if (lane == 0) { col[ck] = 0; typ[ck] = 0; }     // ref :651
             sync();
             // ref :654 snapshot of colour==kk; a cell leaves the snapshot only by deletion (colour -> 0), and a cell
             // that was not in it never gains the colour, so a live test of colour==kk is the same set.
+#pragma unroll 1
             for (int i = lane; i < P; i += L) if (col[i] == kk && typ[i] == 1) typ[i] = (int8_t)tt;  // ref :655-657
-            activate_row_major([&](int i) { return col[i] == kk && not01(typ[i]); });                 // ref :660
-        } else if ((t1 == 2 || t1 == 3) && (t2 == 2 || t2 == 3)) {    // ref :663-674
-            delete_two(i1, i2);
-            const int cell = min(r1, r2) * C + min(c1, c2);
-            activate(cell, 2, false);
-            activate(cell, 3, false);
+            mode = ROWMAJOR; strict = false;                 // ref :660
+        } else if ((t1 == 2 || t1 == 3) && (t2 == 2 || t2 == 3)) {    // ref :663-674: v-laser then h-laser at (r,c)
+            if (lane == 0) { col[i1] = 0; typ[i1] = 0; col[i2] = 0; typ[i2] = 0; }
+            mode = LIST2;
         } else if ((t1 == 4 && (t2 == 2 || t2 == 3)) || (t2 == 4 && (t1 == 2 || t1 == 3))) {  // ref :677-696
-            delete_two(i1, i2);
-            const int r = min(r1, r2), c = min(c1, c2);
-            const int min_r = max(r - 1, 0), max_r = min(r + 1, R - 1);
-            const int min_c = max(c - 1, 0), max_c = min(c + 1, C - 1);
-            for (int i = min_r; i <= max_r; ++i) activate(i * C + c, 3, false);
-            for (int j = min_c; j <= max_c; ++j) activate(r * C + j, 2, false);
+            if (lane == 0) { col[i1] = 0; typ[i1] = 0; col[i2] = 0; typ[i2] = 0; }
+            min_r = max(r - 1, 0); max_r = min(r + 1, R - 1);
+            min_c = max(c - 1, 0); max_c = min(c + 1, C - 1);
+            mode = CROSS;                                    // h-lasers on rows r-1..r+1, then v-lasers on columns c-1..c+1
         } else if (t1 == 4 && t2 == 4) {                     // ref :699-719
-            delete_two(i1, i2);
-            const int r = min(r1, r2), c = min(c1, c2);
-            const int min_r = max(r - 2, 0), max_r = min(r + 2, R - 1);
-            const int min_c = max(c - 2, 0), max_c = min(c + 2, C - 1);
-            const int w = max_c - min_c + 1, n = w * (max_r - min_r + 1);
-            auto cell_of = [&](int i) { return (min_r + i / w) * C + min_c + i % w; };
-            int cur = 0;
-            while (cur < n) {   // row-major: normal -> delete, anything else that is not empty -> activate
-                sync();
-                const int first = first_in_order(cur, n, [&](int i) { const int t = typ[cell_of(i)]; return t != 1 && t != 0; });
+            if (lane == 0) { col[i1] = 0; typ[i1] = 0; col[i2] = 0; typ[i2] = 0; }
+            min_r = max(r - 2, 0); max_r = min(r + 2, R - 1);
+            min_c = max(c - 2, 0); max_c = min(c + 2, C - 1);
+            mode = WINDOW;
+        }
+        const int nr = max_r - min_r + 1, w = max_c - min_c + 1;
+        int cur = 0;
+#pragma unroll 1
+        while (mode != NONE) {
+            sync();
+            int cell = -1, t = 0;
+            if (mode == LIST2) {
+                if (cur < 2) { cell = r * C + c; t = 2 + cur; ++cur; }
+            } else if (mode == CROSS) {
+                if (cur < nr) { cell = (min_r + cur) * C + c; t = 3; ++cur; }
+                else if (cur < nr + w) { cell = r * C + min_c + (cur - nr); t = 2; ++cur; }
+            } else if (mode == ROWMAJOR) {                   // activate_specials_in_mask (ref :721-726)
+                int cand = 1 << 20;
+                if (lane < C) {
+#pragma unroll 1
+                    for (int rr = cur / C; rr < R; ++rr) {
+                        const int i = rr * C + lane;
+                        if (i >= cur && col[i] == kk && (strict ? typ[i] > 1 : not01(typ[i]))) { cand = i; break; }
+                    }
+                }
+                cand = rmin(cand);
+                if (cand < (1 << 20)) { cell = cand; t = typ[cand]; cur = cand + 1; }
+            } else {                                         // 5x5 window, row-major: normal -> delete, other non-empty -> activate
+                const int n = w * nr;
+                auto cell_of = [&](int i) { return (min_r + i / w) * C + min_c + i % w; };
+                const int first = first_in_order(cur, n, [&](int i) { const int tt = typ[cell_of(i)]; return tt != 1 && tt != 0; });
+#pragma unroll 1
                 for (int i = cur + lane; i < first; i += L) {
                     const int q = cell_of(i);
                     if (typ[q] == 1) { col[q] = 0; typ[q] = 0; }
                 }
-                if (first >= n) break;
-                const int q = cell_of(first);
-                const int t = typ[q];
-                sync();
-                activate(q, t, false);
-                cur = first + 1;
+                if (first < n) { cell = cell_of(first); t = typ[cell]; cur = first + 1; }
             }
+            if (cell < 0) break;
+            sync();
+            activate(cell, t, false);
         }
         sync();
     }
@@ -1116,7 +1239,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         is_comb = comb;
         sync();  // every lane has read the swapped types before the leader starts deleting
         if (comb) {
-            combination(i1, i2);                             // ref :361
+            const SlowOut o = slow_combination<L, RT, CT>(&s, &p, lane, gmask, gshift, env, i1, i2);  // ref :361
+            n_new = o.n_new; n_act = o.n_act; status |= o.status;
             int e_cnt;
             const int e = gravity(&e_cnt);                   // ref :362-363
             elim += e_cnt;
@@ -1151,6 +1275,26 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         return ballot(bad) == 0u;
     }
 };
+
+template <int L, int RT, int CT>
+__device__ __noinline__ SlowOut slow_round(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env,
+                                           int n_new, int n_act) {
+    Board<L, RT, CT> b(*sm, *pp, lane, gmask, gshift, env);
+    b.n_new = n_new; b.n_act = n_act;
+    SlowOut o;
+    o.n = b.general_round();
+    o.n_new = b.n_new; o.n_act = b.n_act; o.status = b.status;
+    return o;
+}
+template <int L, int RT, int CT>
+__device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift,
+                                                 int env, int i1, int i2) {
+    Board<L, RT, CT> b(*sm, *pp, lane, gmask, gshift, env);
+    b.combination(i1, i2);
+    SlowOut o;
+    o.n = 0; o.n_new = b.n_new; o.n_act = b.n_act; o.status = b.status;
+    return o;
+}
 
 // ======================================================================================================
 // kernels
@@ -1194,7 +1338,7 @@ template <typename B> __device__ __forceinline__ void merge_status(B& b, const P
 }
 
 // TileMatchEnv.reset (ref tile_match_env.py:84-91) for the selected envs
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(const Params p) {
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     if (p.reset_mask && !p.reset_mask[gc.env]) return;
@@ -1221,7 +1365,10 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 }
 
 // TileMatchEnv.step (ref tile_match_env.py:93-112)
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_step(const Params p) {
+#ifndef TMG_STEP_MIN_BLOCKS
+#define TMG_STEP_MIN_BLOCKS 6   // <= 80 registers/thread: 24 warps/SM (measured +5 % over 128 registers)
+#endif
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_step(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     const int env = gc.env, lane = gc.lane;
@@ -1317,16 +1464,16 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
     merge_status(b, p);
     write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled);
     if (p.prof && lane == 0) {
-        p.prof[env * 4 + 0] = (uint32_t)(clock64() - prof_t0);
-        p.prof[env * 4 + 1] = b.prof_serial;
-        p.prof[env * 4 + 2] = b.prof_rounds;
-        p.prof[env * 4 + 3] = b.prof_iters;
+        p.prof[env * 8 + 0] = (uint32_t)(clock64() - prof_t0);
+        p.prof[env * 8 + 1] = b.prof_serial;
+        p.prof[env * 8 + 2] = b.prof_rounds;
+        p.prof[env * 8 + 3] = b.prof_iters;
     }
 }
 
 // Fills the pool: for every env whose pool entry is not the board after its current one, generate that board
 // (and its mask).  Runs on a side stream, off the step path; touches no env state.
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_pregen(const Params p) {
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     if (p.pool_req[gc.env] != p.pool_tag) return;   // each launch serves exactly the requests tagged for it
@@ -1353,7 +1500,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 }
 
 // _get_effective_actions for every env from its current board (ref tile_match_env.py:118-124)
-template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_mask(const Params p) {
+template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_mask(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     Board<L> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
@@ -1368,7 +1515,7 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_mask(const
 }
 
 // one engine primitive per env (known-answer replays of the reference's function-level tests)
-template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(const Params p) {
+template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
     const int env = gc.env, lane = gc.lane;
