@@ -142,6 +142,7 @@ template <int L, typename V> __device__ __forceinline__ void copy_vec(void* dst,
     const int n = nbytes / (int)sizeof(V);
     V* d = reinterpret_cast<V*>(dst);
     const V* s = reinterpret_cast<const V*>(src);
+#pragma unroll 1
     for (int i = lane; i < n; i += L) d[i] = s[i];
 }
 template <int L> __device__ __noinline__ void copy_bytes(void* dst, const void* src, int nbytes, int vecw, int lane) {
@@ -161,6 +162,12 @@ template <int L> __device__ __forceinline__ void zero_bytes(void* dst, int nbyte
         uint8_t* d = reinterpret_cast<uint8_t*>(dst);
         for (int i = lane; i < nbytes; i += L) d[i] = 0;
     }
+}
+
+// k-th pre-drawn colour of an env in injected mode, -1 when the stream is exhausted
+__device__ __noinline__ int injected_draw(const uint8_t* inj, long long inj_len, int env, long long q) {
+    if (q < inj_len) return inj[(size_t)env * (size_t)inj_len + (size_t)q];
+    return -1;
 }
 
 // is_move_effective (ref :735-787): the literal window rule, evaluated by ONE lane with a virtual swap
@@ -256,6 +263,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     uint32_t status;
     int n_new, n_act;  // counters, uniform after broadcast (ref :343-344)
     uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
+    const uint32_t specials;   // copies of the Params fields the round code needs (no pointer chasing out of line)
+    const bool prof_on;
     // While a board is generated the draws come from the episode-indexed reset streams (see include/tmg_b200.h):
     bool in_reset = false;
     uint32_t episode = 0u;
@@ -264,7 +273,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     __device__ Board(GroupSmem<L>& sm, const Params& pp, int lane_, unsigned gmask_, int gshift_, int env_)
         : s(sm), p(pp), lane(lane_), gmask(gmask_), gshift(gshift_), env(env_), R(RT ? RT : pp.R), C(CT ? CT : pp.C),
           P(RT ? RT * CT : pp.P), K(pp.K), col(sm.board), typ(sm.board + (RT ? RT * CT : pp.P)), dcur(0), scur(0),
-          gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)), status(0), n_new(0), n_act(0) {}
+          gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)), status(0), n_new(0), n_act(0), specials(pp.specials),
+          prof_on(pp.prof != nullptr) {}
 
     // ---- group collectives ---------------------------------------------------------------------------
     __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
@@ -326,10 +336,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         sync();
     }
     __device__ __forceinline__ int injected_colour(int k) {
-        const long long q = (long long)dcur + k;
-        if (q < p.inj_len) return p.inj[(size_t)env * (size_t)p.inj_len + (size_t)q];
-        status |= ST_DRAWS_EXHAUSTED;
-        return 1;
+        const int v = injected_draw(p.inj, p.inj_len, env, (long long)dcur + k);
+        if (v < 0) { status |= ST_DRAWS_EXHAUSTED; return 1; }
+        return v;
     }
     // cells [0, n) in row-major order <- next n draws (initial fill ref :97 / row-block redraw ref :129).
     // Cell i takes word dcur+i, so each lane turns whole Philox blocks straight into board bytes.
@@ -394,6 +403,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             const int nw = min(CF::NW, total - ps);
             if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
             int base = 0;
+#pragma unroll 1
             for (int r = 0; r < maxe; ++r) {
                 const unsigned m = ballot(e > r);
                 if (e > r) {
@@ -762,8 +772,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         uint16_t* out = mlist();
         int qh = 0, qn = n, nslots = n, ncq = 0, ntaken = 0, nm = 0;
         uint32_t flags = 0u;
-        const bool sp_cookie = p.specials & SP_COOKIE, sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER,
-                   sp_bomb = p.specials & SP_BOMB;
+        const bool sp_cookie = specials & SP_COOKIE, sp_v = specials & SP_VLASER, sp_h = specials & SP_HLASER,
+                   sp_bomb = specials & SP_BOMB;
 #pragma unroll 1
         while (qh < qn) {
             const int li = s.order[qh++];                    // ref :285 pop(0)
@@ -905,7 +915,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     __device__ __forceinline__ int fast_round(const Scan& sc) {
         const Bits& b = sc.bits;
         const int rs = sc.rstar;
-        const bool sp_v = p.specials & SP_VLASER, sp_h = p.specials & SP_HLASER;
+        const bool sp_v = specials & SP_VLASER, sp_h = specials & SP_HLASER;
         const unsigned El = from_left(b.E, 1);               // bit r: my left neighbour has my colour
         if (sc.mv == 0u) {                                   // horizontal lines only
             const bool mine = (sc.hcells >> lane) & 1u;
@@ -945,20 +955,20 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // general path of a cascade round: line table, classification, resolution with activations
     __device__ __forceinline__ int general_round() {
         sync();
-        const long long t0 = p.prof ? clock64() : 0;
+        const long long t0 = prof_on ? clock64() : 0;
         const Scan sc = scan_lines(R - 1, false);
         if (sc.rstar < 0) return 0;
-        const long long t1 = p.prof ? clock64() : 0;
+        const long long t1 = prof_on ? clock64() : 0;
         const int n = build_line_table(sc);
-        const long long t2 = p.prof ? clock64() : 0;
+        const long long t2 = prof_on ? clock64() : 0;
         uint32_t packed = 0u;
         if (lane == 0) packed = classify_lines(n);
         packed = (uint32_t)shfl((int)packed, 0);
         sync();
-        const long long t3 = p.prof ? clock64() : 0;
+        const long long t3 = prof_on ? clock64() : 0;
         resolve_matches(packed);
         sync();
-        if (p.prof && lane == 0) {   // diagnostics: cycles per phase of the general path, accumulated per env
+        if (prof_on && lane == 0) {   // diagnostics: cycles per phase of the general path, accumulated per env
             const long long t4 = clock64();
             atomicAdd(&p.prof[env * 8 + 4], (uint32_t)(t1 - t0));
             atomicAdd(&p.prof[env * 8 + 5], (uint32_t)(t2 - t1));
@@ -976,10 +986,10 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         ++prof_rounds;
         int n = fast_round(sc);
         if (n == 0) {
-            const long long t0 = p.prof ? clock64() : 0;
+            const long long t0 = prof_on ? clock64() : 0;
             const SlowOut o = slow_round<L, RT, CT>(&s, &p, lane, gmask, gshift, env, n_new, n_act);
             n = o.n; n_new = o.n_new; n_act = o.n_act; status |= o.status;
-            if (p.prof) prof_serial += (uint32_t)(clock64() - t0);
+            if (prof_on) prof_serial += (uint32_t)(clock64() - t0);
         }
         sync();
         return n;
