@@ -105,12 +105,13 @@ template <int L> struct __align__(16) GroupSmem {
     uint32_t wbuf[4 * L];            // stream words of the current Philox pass
     uint32_t stack[Cfg<L>::DFS];     // activation DFS frames
     uint32_t line_key[Cfg<L>::ML];   // (top row << 12) | list position  -> processing order
-    uint16_t line_cells[Cfg<L>::ML][Cfg<L>::MLEN];
+    uint32_t line_mask[Cfg<L>::ML];  // a line is straight: its columns (horizontal) or rows (vertical) as a bit set
     uint16_t match[Cfg<L>::MLEN + 4];
     uint16_t cq_pos[Cfg<L>::ML];     // special-creation queue (ref :411)
     uint16_t taken[Cfg<L>::ML];
     uint16_t cnt[32];                // colour histogram for the cookie (ref :536)
-    uint8_t line_len[Cfg<L>::ML];
+    uint8_t line_kind[Cfg<L>::ML];   // 0 horizontal (line_idx = row), 1 vertical (line_idx = column)
+    uint8_t line_idx[Cfg<L>::ML];
     uint8_t line_colour[Cfg<L>::ML];
     uint8_t order[Cfg<L>::ML];
     int8_t cq_type[Cfg<L>::ML];
@@ -508,10 +509,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         if (sc.has_v) {
             const int slot = before;
             if (slot < CF::ML) {
-                const int len = rs - sc.vtop + 1;
-#pragma unroll 1
-                for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)((sc.vtop + k) * C + lane);
-                s.line_len[slot] = (uint8_t)len;
+                s.line_mask[slot] = ((2u << rs) - 1u) & ~((1u << sc.vtop) - 1u);   // rows vtop..rs
+                s.line_kind[slot] = 1;
+                s.line_idx[slot] = (uint8_t)lane;
                 s.line_colour[slot] = (uint8_t)col[rs * C + lane];
                 s.line_key[slot] = ((uint32_t)sc.vtop << 12) | (uint32_t)slot;
             }
@@ -520,9 +520,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             const int slot = before + (sc.has_v ? 1 : 0);
             if (slot < CF::ML) {
                 const int run = __ffs((int)~(sc.m >> lane)) - 1;
-#pragma unroll 1
-                for (int k = 0; k <= run; ++k) s.line_cells[slot][k] = (uint16_t)(rs * C + lane + k);
-                s.line_len[slot] = (uint8_t)(run + 1);
+                s.line_mask[slot] = ((2u << run) - 1u) << lane;                        // columns lane..lane+run
+                s.line_kind[slot] = 0;
+                s.line_idx[slot] = (uint8_t)rs;
                 s.line_colour[slot] = (uint8_t)col[rs * C + lane];
                 s.line_key[slot] = ((uint32_t)rs << 12) | (uint32_t)slot;
             }
@@ -551,10 +551,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                 if (seg) {
                     const int slot = n + __popc(segm & lt);
                     if (slot < CF::ML) {
-                        const int len = 1 + left + right;
-#pragma unroll 1
-                        for (int k = 0; k < len; ++k) s.line_cells[slot][k] = (uint16_t)(r * C + lane - left + k);
-                        s.line_len[slot] = (uint8_t)len;
+                        s.line_mask[slot] = ((2u << (left + right)) - 1u) << (lane - left);   // columns lane-left..lane+right
+                        s.line_kind[slot] = 0;
+                        s.line_idx[slot] = (uint8_t)r;
                         s.line_colour[slot] = (uint8_t)col[r * C + lane];
                         // same top row: phase 1 first, then phase 2 by (column of the vertical line, row)
                         s.line_key[slot] = ((uint32_t)r << 12) | (uint32_t)(1024 + lane * 32 + r);
@@ -707,55 +706,53 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         sync();
     }
 
-    // get_special_creation_pos (ref :429-458) on s.match[0..n); leader lane
-    __device__ __forceinline__ int creation_pos(int n, int ntaken, bool straight) {
+    // get_special_creation_pos for a bomb (ref :441-450) on s.match[0..n); leader lane
+    __device__ __forceinline__ int creation_pos_bomb(int n, int ntaken) {
         auto is_taken = [&](int cell) {
 #pragma unroll 1
             for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
             return false;
         };
-        int nv = 0;
+        int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
 #pragma unroll 1
-        for (int k = 0; k < n; ++k) nv += !is_taken(s.match[k]);
-        if (nv == 0) return -1;                                 // reference: IndexError
-        if (!straight) {                                        // ref :441-450
-            int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
+        for (int k = 0; k < n; ++k) {                       // max(xs, key=xs.count): first element with the top count
+            const int rr = s.match[k] / C, cc = s.match[k] % C;
+            int nr = 0, nc = 0;
 #pragma unroll 1
-            for (int k = 0; k < n; ++k) {                       // max(xs, key=xs.count): first element with the top count
-                const int rr = s.match[k] / C, cc = s.match[k] % C;
-                int nr = 0, nc = 0;
-#pragma unroll 1
-                for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
-                if (nr > best_rc) { best_rc = nr; best_r = rr; }
-                if (nc > best_cc) { best_cc = nc; best_c = cc; }
-            }
-            const int corner = best_r * C + best_c;
-            int best = -1, bestd = 0;
-#pragma unroll 1
-            for (int k = 0; k < n; ++k) {
-                const int cell = s.match[k];
-                if (is_taken(cell)) continue;
-                if (cell == corner) return corner;              // ref :446-447
-                const int dr = cell / C - best_r, dc = cell % C - best_c, d = dr * dr + dc * dc;
-                if (best < 0 || d < bestd) { best = cell; bestd = d; }  // stable: first minimum (ref :449)
-            }
-            return best;
+            for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
+            if (nr > best_rc) { best_rc = nr; best_r = rr; }
+            if (nc > best_cc) { best_cc = nc; best_c = cc; }
         }
-        // straight: the match is already sorted by (row, col); pick the middle of the valid cells (ref :453-458)
-        const int want = (nv % 2 == 0) ? nv / 2 - 1 : nv / 2;
-        int seen = 0;
+        const int corner = best_r * C + best_c;
+        int best = -1, bestd = 0;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-            if (is_taken(s.match[k])) continue;
-            if (seen == want) return s.match[k];
-            ++seen;
+            const int cell = s.match[k];
+            if (is_taken(cell)) continue;
+            if (cell == corner) return corner;              // ref :446-447
+            const int dr = cell / C - best_r, dc = cell % C - best_c, d = dr * dr + dc * dc;
+            if (best < 0 || d < bestd) { best = cell; bestd = d; }  // stable: first minimum (ref :449)
         }
-        return -1;
+        return best;                                        // -1: no valid cell (reference: IndexError)
     }
 
     // process_colour_lines (ref :269-327) + the creation cells of resolve_colour_matches (ref :414-418); leader lane.
-    // Writes the cells of all matches, in resolve order, to mlist() and the creation queue to s.cq_*.
-    // Returns nm | ncq << 16 | flags << 24 (flag 1: table overflow, flag 2: no valid creation cell).
+    // Lines are straight (also after a bomb took cells out of them), so a line is (kind, row|column, bit set) and
+    // "do these two lines share a cell" is two bit tests.  Writes the cells of all matches, in resolve order, to
+    // mlist() and the creation queue to s.cq_*.  Returns nm | ncq << 16 | flags << 24 (flag 1: table overflow,
+    // flag 2: no valid creation cell).
+    __device__ __forceinline__ int line_cell(int kind, int idx, int bit) const { return kind ? bit * C + idx : idx * C + bit; }
+    __device__ __forceinline__ static unsigned lowest_bits(unsigned m, int k) {   // the k lowest set bits of m
+        unsigned out = 0u;
+#pragma unroll 1
+        for (int i = 0; i < k && m; ++i) { const unsigned b = m & (0u - m); out |= b; m ^= b; }
+        return out;
+    }
+    __device__ __forceinline__ static int nth_bit(unsigned m, int k) {            // position of the k-th (0-based) set bit
+#pragma unroll 1
+        for (int i = 0; i < k; ++i) m &= m - 1u;
+        return __ffs((int)m) - 1;
+    }
     __device__ __forceinline__ uint32_t classify_lines(int n) {
         // ref :282: stable sort by the first cell's row == sort by key (keys are unique)
 #pragma unroll 1
@@ -777,89 +774,107 @@ template <int L, int RT = 0, int CT = 0> struct Board {
 #pragma unroll 1
         while (qh < qn) {
             const int li = s.order[qh++];                    // ref :285 pop(0)
-            const int len = s.line_len[li];
-            const uint16_t* cells = s.line_cells[li];
-            int mlen = 0, name = NAME_NORMAL, colour = s.line_colour[li];
-            bool have = false;
+            const int kind = s.line_kind[li], idx = s.line_idx[li];
+            const unsigned mask = s.line_mask[li];
+            const int len = __popc(mask);
+            int name = NAME_NORMAL, colour = s.line_colour[li];
+            unsigned mm = 0u;                                // cells of the match that lie on this line
+            int extra[3] = {-1, -1, -1}, nextra = 0;         // bomb: cells taken from the crossing line
             if (len >= 5 && sp_cookie) {                     // ref :287-292
-#pragma unroll 1
-                for (int k = 0; k < 5; ++k) s.match[mlen++] = cells[k];
-                name = NAME_COOKIE; colour = 0; have = true;
-                if (len - 5 > 2) {
+                mm = lowest_bits(mask, 5);
+                name = NAME_COOKIE; colour = 0;
+                const unsigned rest = mask & ~mm;
+                if (__popc(rest) > 2) {
                     if (nslots < CF::ML && qn < CF::ML) {
                         const int ns = nslots++;
-#pragma unroll 1
-                        for (int k = 5; k < len; ++k) s.line_cells[ns][k - 5] = cells[k];
-                        s.line_len[ns] = (uint8_t)(len - 5);
+                        s.line_mask[ns] = rest; s.line_kind[ns] = (uint8_t)kind; s.line_idx[ns] = (uint8_t)idx;
                         s.line_colour[ns] = s.line_colour[li];
                         s.order[qn++] = (uint8_t)ns;
                     } else flags |= 1u;
                 }
             } else if (len == 4) {                           // ref :294-302
-#pragma unroll 1
-                for (int k = 0; k < 4; ++k) s.match[mlen++] = cells[k];
-                const bool horizontal = (cells[0] / C) == (cells[1] / C);
-                name = (horizontal && sp_h) ? NAME_HLASER : (sp_v ? NAME_VLASER : NAME_NORMAL);
-                have = true;
+                mm = mask;
+                name = (kind == 0 && sp_h) ? NAME_HLASER : (sp_v ? NAME_VLASER : NAME_NORMAL);
             } else {
-                int hit = -1, shared = -1;
+                int hit = -1, spos = 0;                      // spos: position of the shared cell along the crossing line
                 if (sp_bomb) {                               // ref :304-308: first queued line sharing a cell
 #pragma unroll 1
-                    for (int q = qh; q < qn && hit < 0; ++q) {
+                    for (int q = qh; q < qn; ++q) {
                         const int lj = s.order[q];
-#pragma unroll 1
-                        for (int k = 0; k < len && hit < 0; ++k)
-#pragma unroll 1
-                            for (int u = 0; u < s.line_len[lj]; ++u)
-                                if (s.line_cells[lj][u] == cells[k]) { hit = q; shared = cells[k]; break; }
+                        const int k2 = s.line_kind[lj], i2 = s.line_idx[lj];
+                        const unsigned m2 = s.line_mask[lj];
+                        if (k2 != kind) {                    // a row and a column meet in one cell
+                            if (((mask >> i2) & 1u) && ((m2 >> idx) & 1u)) { hit = q; spos = idx; break; }
+                        } else if (i2 == idx && (mask & m2)) { // same row (crossing segments can overlap)
+                            hit = q; spos = __ffs((int)(mask & m2)) - 1; break;   // first cell of `line` that is in l
+                        }
                     }
                 }
                 if (hit >= 0) {                              // ref :309-320
                     const int lj = s.order[hit];
-                    const int llen = s.line_len[lj];
-                    uint16_t* lc = s.line_cells[lj];
-                    const int sr = shared / C, scc = shared % C;
+                    const int k2 = s.line_kind[lj], i2 = s.line_idx[lj];
+                    unsigned m2 = s.line_mask[lj];
+                    const int llen = __popc(m2);
+                    mm = mask;
+                    // ref :310-312: the three cells of l closest to the shared cell (stable: lower position first on ties)
+                    unsigned picked = 0u;
 #pragma unroll 1
-                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
-                    // first three of the stable sort of l by Manhattan distance (ref :310)
-                    int picked[3] = {-1, -1, -1};
-                    const int take = llen < 3 ? llen : 3;
+                    for (int d = 0; d < 32 && __popc(picked) < 3 && picked != m2; ++d) {
 #pragma unroll 1
-                    for (int a = 0; a < take; ++a) {
-                        int bi = -1, bd = 0;
-#pragma unroll 1
-                        for (int u = 0; u < llen; ++u) {
-                            if (u == picked[0] || u == picked[1]) continue;
-                            const int d = abs(lc[u] / C - sr) + abs(lc[u] % C - scc);
-                            if (bi < 0 || d < bd) { bi = u; bd = d; }
+                        for (int sgn = 0; sgn < (d ? 2 : 1); ++sgn) {
+                            const int pos = sgn ? spos + d : spos - d;
+                            if (pos < 0 || pos > 31 || !((m2 >> pos) & 1u) || __popc(picked) >= 3) continue;
+                            picked |= 1u << pos;
+                            const bool in_line = (k2 != kind) ? (pos == idx) : (((mask >> pos) & 1u) != 0u);
+                            if (!in_line) extra[nextra++] = line_cell(k2, i2, pos);
                         }
-                        picked[a] = bi;
-                        bool in_line = false;
-#pragma unroll 1
-                        for (int k = 0; k < len; ++k) in_line |= (cells[k] == lc[bi]);
-                        if (!in_line) s.match[mlen++] = lc[bi];  // ref :312
                     }
-                    name = NAME_BOMB; have = true;
+                    name = NAME_BOMB;
                     if (llen < 6) {                          // ref :315-316 (lines are distinct by value)
 #pragma unroll 1
                         for (int q = hit; q + 1 < qn; ++q) s.order[q] = s.order[q + 1];
                         --qn;
-                    } else {                                 // ref :317-319: drop the three cells, keep the order
-                        int w = 0;
-#pragma unroll 1
-                        for (int u = 0; u < llen; ++u)
-                            if (u != picked[0] && u != picked[1] && u != picked[2]) lc[w++] = lc[u];
-                        s.line_len[lj] = (uint8_t)w;
+                    } else {                                 // ref :317-319: drop the three cells
+                        s.line_mask[lj] = m2 & ~picked;
                     }
                 } else if (len >= 3) {                       // ref :322-325
+                    mm = mask;
+                } else continue;
+            }
+            // cells of the match in list order: the line's cells ascending, then the bomb's extra cells (ref :312)
+            const int first_out = nm;
+            {
+                unsigned t = mm;
 #pragma unroll 1
-                    for (int k = 0; k < len; ++k) s.match[mlen++] = cells[k];
-                    have = true;
+                while (t) {
+                    const int bit = __ffs((int)t) - 1;
+                    t &= t - 1u;
+                    if (nm < MCAP) out[nm++] = (uint16_t)line_cell(kind, idx, bit);
+                    else flags |= 1u;
+                }
+#pragma unroll 1
+                for (int k = 0; k < nextra; ++k) {
+                    if (nm < MCAP) out[nm++] = (uint16_t)extra[k];
+                    else flags |= 1u;
                 }
             }
-            if (!have) continue;
             if (name != NAME_NORMAL) {                       // ref :414-418
-                const int pos = creation_pos(mlen, ntaken, name != NAME_BOMB);
+                int pos;
+                if (name == NAME_BOMB) {
+                    const int cnt = nm - first_out;
+#pragma unroll 1
+                    for (int k = 0; k < cnt && k < CF::MLEN + 4; ++k) s.match[k] = out[first_out + k];
+                    pos = creation_pos_bomb(min(cnt, CF::MLEN + 4), ntaken);
+                } else {                                     // straight: middle of the valid cells (ref :453-458)
+                    unsigned valid = mm;
+#pragma unroll 1
+                    for (int q = 0; q < ntaken; ++q) {
+                        const int tc = s.taken[q], tr = tc / C, tcol = tc - tr * C;
+                        if (kind == 0 ? tr == idx : tcol == idx) valid &= ~(1u << (kind == 0 ? tcol : tr));
+                    }
+                    const int nv = __popc(valid);
+                    pos = nv ? line_cell(kind, idx, nth_bit(valid, (nv % 2 == 0) ? nv / 2 - 1 : nv / 2)) : -1;
+                }
                 if (pos < 0) flags |= 2u;
                 if (pos >= 0 && ntaken < CF::ML) s.taken[ntaken++] = (uint16_t)pos;
                 if (ncq < CF::ML) {
@@ -868,11 +883,6 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                     s.cq_colour[ncq] = (uint8_t)colour;
                     ++ncq;
                 }
-            }
-#pragma unroll 1
-            for (int k = 0; k < mlen; ++k) {                 // cells in resolve order (ref :421-423, :467)
-                if (nm < MCAP) out[nm++] = s.match[k];
-                else flags |= 1u;
             }
         }
         return (uint32_t)nm | ((uint32_t)ncq << 16) | (flags << 24);
