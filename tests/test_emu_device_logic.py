@@ -43,3 +43,79 @@ def test_emulated_batch_vs_oracle(cfg):
         e.step(a); o.step(a)
         for f in fields:
             assert np.array_equal(getattr(e, f), getattr(o, f)), (t, f)
+
+
+# ----------------------------------------------------------------------------------------------
+# primitive-level differential fuzz: one engine primitive on random boards (dense specials, few colours so that
+# crossings / long lines / chains are common), device code (emulated) vs oracle, for several special subsets
+OPS = dict(GRAVITY=1, REFILL=2, RESOLVE=3, ACTIVATE=4, COMBINE=5, MOVE=6, EFFECTIVE=7, GENERATE=8, SHUFFLE=9, COUNT=10)
+SUBSETS = [(("cookie",), ("vertical_laser", "horizontal_laser", "bomb")), ((), ("bomb",)), (("cookie",), ("horizontal_laser",)),
+           ((), ("vertical_laser",)), ((), ())]
+
+
+def _rand_board(rng, R, C, K, ps, pc, pe=0.0):
+    col = rng.integers(1, K + 1, (R, C)); typ = np.ones((R, C), int)
+    u = rng.random((R, C)); typ[u < ps] = rng.integers(2, 5, (R, C))[u < ps]
+    ck = rng.random((R, C)) < pc; typ[ck] = -1; col[ck] = 0
+    em = rng.random((R, C)) < pe; typ[em] = 0; col[em] = 0
+    return np.stack([col, typ]).astype(np.int32)
+
+
+@pytest.mark.parametrize("which,R,C,K,iters", [
+    ("RESOLVE", 7, 7, 3, 60), ("RESOLVE", 6, 12, 2, 60), ("RESOLVE", 10, 10, 4, 40), ("MOVE", 10, 10, 4, 40),
+    ("MOVE", 5, 4, 2, 60), ("COMBINE", 7, 7, 3, 60), ("COMBINE", 10, 10, 4, 40), ("ACTIVATE", 9, 9, 6, 40),
+    ("GRAVITY", 7, 9, 3, 30), ("REFILL", 7, 9, 3, 30), ("MASK", 10, 10, 4, 30), ("COUNT", 12, 6, 2, 40),
+])
+def test_emulated_primitives_vs_oracle(which, R, C, K, iters):
+    rng = np.random.default_rng(hash((which, R, C)) % 2**32)
+    for si, (cl, cs) in enumerate(SUBSETS):
+        e = EmuVecEnv(1, R, C, K, 1000, cl, cs, seed=11, env_id_offset=7)
+        for it in range(iters // len(SUBSETS) + 1):
+            b = _rand_board(rng, R, C, K, 0.15, 0.05, pe=(0.2 if which in ("GRAVITY", "REFILL") else 0.0))
+            o = orc.OracleBoard(R, C, K, cl, cs, seed=11, env_id=7, board=b)
+            e.reset(init_boards=b.astype(np.int8)[None])
+            e.status[:] = 0
+            dc = int(rng.integers(0, 1000)); e.draw_cursor[0] = dc; o.set_stream(11, 7, dc, 0)
+            e.num_new_specials[0] = 0; e.num_specials_activated[0] = 0; o.set_counters(0, 0)
+            args = np.zeros((1, 4), np.int32)
+            counters = lambda: (int(e.num_new_specials[0]), int(e.num_specials_activated[0]))  # noqa: E731
+            if which == "COUNT":
+                e.debug_op(OPS["COUNT"], args)
+                assert len(o.get_colour_lines()) == int(e.reward[0])
+                continue
+            if which == "MASK":
+                e.legal_mask()
+                assert np.array_equal(o.effective_mask(), e.mask[0])
+                continue
+            if which == "RESOLVE":
+                o.resolve_round(); e.debug_op(OPS["RESOLVE"], args)
+            elif which == "ACTIVATE":
+                sp = np.argwhere((b[1] != 0) & (b[1] != 1))
+                if len(sp) == 0:
+                    continue
+                r, c = sp[rng.integers(len(sp))]; comb = int(rng.integers(2))
+                o.activate_special((r, c), b[1, r, c], b[0, r, c], bool(comb)); args[0] = [r, c, b[1, r, c], comb]
+                e.debug_op(OPS["ACTIVATE"], args)
+            elif which == "COMBINE":
+                cands = [a for a in range(o.num_actions)
+                         if (lambda t1, t2: (t1 not in (0, 1) and t2 not in (0, 1)) or t1 < 0 or t2 < 0)(
+                             b[1][o.action_to_coords[a][0]], b[1][o.action_to_coords[a][1]])]
+                if not cands:
+                    continue
+                (r1, c1), (r2, c2) = o.action_to_coords[cands[rng.integers(len(cands))]]
+                o.combination_match((r1, c1), (r2, c2)); args[0] = [r1, c1, r2, c2]; e.debug_op(OPS["COMBINE"], args)
+            elif which == "GRAVITY":
+                o.gravity(); e.debug_op(OPS["GRAVITY"], args)
+            elif which == "REFILL":
+                o.refill(); e.debug_op(OPS["REFILL"], args)
+                assert o.cursors[0] == int(e.draw_cursor[0])
+            elif which == "MOVE":
+                (r1, c1), (r2, c2) = o.action_to_coords[int(rng.integers(o.num_actions))]
+                want = o.move((r1, c1), (r2, c2)); args[0] = [r1, c1, r2, c2]; e.debug_op(OPS["MOVE"], args)
+                got = (int(e.reward[0]), bool(e.is_combination_match[0]), *counters(), bool(e.shuffled[0]))
+                assert want == got, (want, got)
+                assert o.cursors == (int(e.draw_cursor[0]), int(e.shuffle_cursor[0]))
+            assert np.array_equal(o.board.astype(np.int8), e.board[0]), (which, si, it)
+            if which in ("RESOLVE", "ACTIVATE", "COMBINE"):
+                assert o.counters == counters(), (which, si, it)
+            assert int(e.status[0]) == 0

@@ -26,6 +26,7 @@ struct tmg_env {
     cudaStream_t side[SIDE];
     cudaEvent_t ev_step, ev_pregen[RING];
     long long pregen_count;   // number of k_pregen launches so far
+    int pregen_grid_cap;      // blocks per k_pregen launch: about half of the resident-block slots of the device
     bool pregen;              // pool in use (philox refill, not disabled by flag)
 };
 
@@ -53,6 +54,14 @@ int check_device(int device) {
 template <int L_, int R_, int C_> struct Shape { static constexpr int L = L_, R = R_, C = C_; };
 template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
     const int R = e->p.R, C = e->p.C;
+    static const bool generic_only = getenv("TMG_B200_GENERIC_SHAPES") != nullptr;   // diagnostics: skip the fixed-shape kernels
+    if (generic_only) {
+        switch (e->L) {
+            case 8: return f(Shape<8, 0, 0>());
+            case 16: return f(Shape<16, 0, 0>());
+            default: return f(Shape<32, 0, 0>());
+        }
+    }
     if (R == 10 && C == 10) return f(Shape<16, 10, 10>());
     if (R == 9 && C == 9) return f(Shape<16, 9, 9>());
     if (R == 32 && C == 32) return f(Shape<32, 32, 32>());
@@ -100,7 +109,9 @@ static int launch_pregen(tmg_env* e, cudaStream_t st) {
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
-        k_pregen<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), side>>>(p);
+        const int full = grid_for<L>(p.N);
+        const int cap = e->pregen_grid_cap;
+        k_pregen<L, S::R, S::C><<<full < cap ? full : cap, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), side>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
@@ -226,6 +237,13 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.pool_req = reinterpret_cast<int32_t*>(b + o_pool_req);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
+    {
+        // tuning knob: cap the refill kernel to this many blocks per SM.  Measured on B200 (65 536 envs): uncapped is
+        // best overall -- a capped refill delays fewer steps but runs longer beside more of them.
+        const char* capenv = getenv("TMG_B200_PREGEN_BLOCKS_PER_SM");
+        const int per_sm = capenv ? atoi(capenv) : 0;
+        e->pregen_grid_cap = per_sm > 0 ? prop.multiProcessorCount * per_sm : 0x7fffffff;
+    }
     for (int i = 0; i < tmg_env::SIDE; ++i) e->side[i] = nullptr;
     bool ok = cudaMemset(p.episode, 0xff, (size_t)N * 4) == cudaSuccess &&       // -1: no board generated yet
               cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess &&  // never equal to a real episode

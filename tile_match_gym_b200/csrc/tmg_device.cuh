@@ -106,7 +106,6 @@ template <int L> struct __align__(16) GroupSmem {
     uint32_t stack[Cfg<L>::DFS];     // activation DFS frames
     uint32_t line_key[Cfg<L>::ML];   // (top row << 12) | list position  -> processing order
     uint32_t line_mask[Cfg<L>::ML];  // a line is straight: its columns (horizontal) or rows (vertical) as a bit set
-    uint16_t match[Cfg<L>::MLEN + 4];
     uint16_t cq_pos[Cfg<L>::ML];     // special-creation queue (ref :411)
     uint16_t taken[Cfg<L>::ML];
     uint16_t cnt[32];                // colour histogram for the cookie (ref :536)
@@ -240,9 +239,12 @@ __device__ __noinline__ void shuffle_serial(int8_t* col, int8_t* typ, int P, uin
 // The rare, large parts of a cascade round run out of line on a private Board view, so that the common round
 // (scan, fast path, gravity, refill) stays small enough for the instruction caches.
 struct SlowOut { int n, n_new, n_act; uint32_t status; };
+struct SlowScan {   // Board::Scan by value
+    int rstar; unsigned mv, hs, hcells, m; int vtop; bool has_v; unsigned E, D, T, S;
+};
 template <int L, int RT, int CT>
 __device__ __noinline__ SlowOut slow_round(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env,
-                                           int n_new, int n_act);
+                                           int n_new, int n_act, SlowScan sc);
 template <int L, int RT, int CT>
 __device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift,
                                                  int env, int i1, int i2);
@@ -706,31 +708,28 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         sync();
     }
 
-    // get_special_creation_pos for a bomb (ref :441-450) on s.match[0..n); leader lane
-    __device__ __forceinline__ int creation_pos_bomb(int n, int ntaken) {
+    // get_special_creation_pos for a bomb (ref :441-450); leader lane.  The match is a straight line plus up to three
+    // cells of the crossing line, listed as out[0..n): the modal row / column (first element with the top count,
+    // ref :445) follow from the geometry -- all cells of a horizontal line share its row, and the crossing column is
+    // the only column that can repeat (shared cell + extra cells) -- so no counting is needed.
+    __device__ __forceinline__ int creation_pos_bomb(const uint16_t* cells, int n, int ntaken, int kind, int idx, int k2, int i2,
+                                                     int first_bit, int nextra) {
+        int mrow, mcol;
+        if (kind == 0) { mrow = idx; mcol = (k2 != kind && nextra >= 1) ? i2 : first_bit; }
+        else { mcol = idx; mrow = (k2 != kind && nextra >= 1) ? i2 : first_bit; }
+        const int corner = mrow * C + mcol;
         auto is_taken = [&](int cell) {
 #pragma unroll 1
             for (int q = 0; q < ntaken; ++q) if (s.taken[q] == cell) return true;
             return false;
         };
-        int best_r = -1, best_rc = 0, best_c = -1, best_cc = 0;
-#pragma unroll 1
-        for (int k = 0; k < n; ++k) {                       // max(xs, key=xs.count): first element with the top count
-            const int rr = s.match[k] / C, cc = s.match[k] % C;
-            int nr = 0, nc = 0;
-#pragma unroll 1
-            for (int q = 0; q < n; ++q) { nr += (s.match[q] / C == rr); nc += (s.match[q] % C == cc); }
-            if (nr > best_rc) { best_rc = nr; best_r = rr; }
-            if (nc > best_cc) { best_cc = nc; best_c = cc; }
-        }
-        const int corner = best_r * C + best_c;
+        if (!is_taken(corner)) return corner;               // ref :446-447 (the corner is always a cell of the match)
         int best = -1, bestd = 0;
 #pragma unroll 1
         for (int k = 0; k < n; ++k) {
-            const int cell = s.match[k];
+            const int cell = cells[k];
             if (is_taken(cell)) continue;
-            if (cell == corner) return corner;              // ref :446-447
-            const int dr = cell / C - best_r, dc = cell % C - best_c, d = dr * dr + dc * dc;
+            const int dr = cell / C - mrow, dc = cell % C - mcol, d = dr * dr + dc * dc;
             if (best < 0 || d < bestd) { best = cell; bestd = d; }  // stable: first minimum (ref :449)
         }
         return best;                                        // -1: no valid cell (reference: IndexError)
@@ -780,6 +779,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             int name = NAME_NORMAL, colour = s.line_colour[li];
             unsigned mm = 0u;                                // cells of the match that lie on this line
             int extra[3] = {-1, -1, -1}, nextra = 0;         // bomb: cells taken from the crossing line
+            int bomb_k2 = 0, bomb_i2 = 0;
             if (len >= 5 && sp_cookie) {                     // ref :287-292
                 mm = lowest_bits(mask, 5);
                 name = NAME_COOKIE; colour = 0;
@@ -816,6 +816,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                     unsigned m2 = s.line_mask[lj];
                     const int llen = __popc(m2);
                     mm = mask;
+                    bomb_k2 = k2; bomb_i2 = i2;
                     // ref :310-312: the three cells of l closest to the shared cell (stable: lower position first on ties)
                     unsigned picked = 0u;
 #pragma unroll 1
@@ -861,10 +862,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             if (name != NAME_NORMAL) {                       // ref :414-418
                 int pos;
                 if (name == NAME_BOMB) {
-                    const int cnt = nm - first_out;
-#pragma unroll 1
-                    for (int k = 0; k < cnt && k < CF::MLEN + 4; ++k) s.match[k] = out[first_out + k];
-                    pos = creation_pos_bomb(min(cnt, CF::MLEN + 4), ntaken);
+                    pos = creation_pos_bomb(out + first_out, nm - first_out, ntaken, kind, idx, bomb_k2, bomb_i2,
+                                            __ffs((int)mm) - 1, nextra);
                 } else {                                     // straight: middle of the valid cells (ref :453-458)
                     unsigned valid = mm;
 #pragma unroll 1
@@ -963,10 +962,8 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     }
 
     // general path of a cascade round: line table, classification, resolution with activations
-    __device__ __forceinline__ int general_round() {
-        sync();
+    __device__ __forceinline__ int general_round(const Scan& sc) {
         const long long t0 = prof_on ? clock64() : 0;
-        const Scan sc = scan_lines(R - 1, false);
         if (sc.rstar < 0) return 0;
         const long long t1 = prof_on ? clock64() : 0;
         const int n = build_line_table(sc);
@@ -997,7 +994,10 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         int n = fast_round(sc);
         if (n == 0) {
             const long long t0 = prof_on ? clock64() : 0;
-            const SlowOut o = slow_round<L, RT, CT>(&s, &p, lane, gmask, gshift, env, n_new, n_act);
+            SlowScan ss;
+            ss.rstar = sc.rstar; ss.mv = sc.mv; ss.hs = sc.hs; ss.hcells = sc.hcells; ss.m = sc.m; ss.vtop = sc.vtop; ss.has_v = sc.has_v;
+            ss.E = sc.bits.E; ss.D = sc.bits.D; ss.T = sc.bits.T; ss.S = sc.bits.S;
+            const SlowOut o = slow_round<L, RT, CT>(&s, &p, lane, gmask, gshift, env, n_new, n_act, ss);
             n = o.n; n_new = o.n_new; n_act = o.n_act; status |= o.status;
             if (prof_on) prof_serial += (uint32_t)(clock64() - t0);
         }
@@ -1298,11 +1298,14 @@ template <int L, int RT = 0, int CT = 0> struct Board {
 
 template <int L, int RT, int CT>
 __device__ __noinline__ SlowOut slow_round(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env,
-                                           int n_new, int n_act) {
+                                           int n_new, int n_act, SlowScan ss) {
     Board<L, RT, CT> b(*sm, *pp, lane, gmask, gshift, env);
     b.n_new = n_new; b.n_act = n_act;
+    typename Board<L, RT, CT>::Scan sc;
+    sc.rstar = ss.rstar; sc.mv = ss.mv; sc.hs = ss.hs; sc.hcells = ss.hcells; sc.m = ss.m; sc.vtop = ss.vtop; sc.has_v = ss.has_v;
+    sc.bits.E = ss.E; sc.bits.D = ss.D; sc.bits.T = ss.T; sc.bits.S = ss.S;
     SlowOut o;
-    o.n = b.general_round();
+    o.n = b.general_round(sc);
     o.n_new = b.n_new; o.n_act = b.n_act; o.status = b.status;
     return o;
 }
@@ -1494,29 +1497,33 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 // Fills the pool: for every env whose pool entry is not the board after its current one, generate that board
 // (and its mask).  Runs on a side stream, off the step path; touches no env state.
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
+    // Launched with a capped grid (about half of the resident-block slots) so that the step kernels always find free
+    // slots beside it; every group walks its share of the envs.
     const GroupCtx<L> gc;
-    if (gc.env >= p.N) return;
-    if (p.pool_req[gc.env] != p.pool_tag) return;   // each launch serves exactly the requests tagged for it
-    const int ep = p.episode[gc.env] + 1;
-    if (p.pool_episode[gc.env] == ep) return;
-    Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
-    unsigned effv = 0u, effh = 0u;
-    b.sync();
-    b.begin_generate((uint32_t)ep);
-    b.playability(false, true, effv, effh);
-    b.end_generate();
-    b.sync();
-    copy_bytes<L>(p.pool_board + (size_t)gc.env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, gc.lane);
-    if (!(p.flags & FLAG_NO_MASK)) {
-        b.mask_to_smem(effv, effh);
+    for (int env = gc.env; env < p.N; env += (int)gridDim.x * Cfg<L>::GPB) {
+        if (p.pool_req[env] != p.pool_tag) continue;   // each launch serves exactly the requests tagged for it
+        const int ep = p.episode[env] + 1;
+        if (p.pool_episode[env] == ep) continue;
+        Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, env);
+        unsigned effv = 0u, effh = 0u;
         b.sync();
-        copy_bytes<L>(p.pool_mask + (size_t)gc.env * p.A, b.s.mask, p.A, p.mask_vecw, gc.lane);
+        b.begin_generate((uint32_t)ep);
+        b.playability(false, true, effv, effh);
+        b.end_generate();
+        b.sync();
+        copy_bytes<L>(p.pool_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, gc.lane);
+        if (!(p.flags & FLAG_NO_MASK)) {
+            b.mask_to_smem(effv, effh);
+            b.sync();
+            copy_bytes<L>(p.pool_mask + (size_t)env * p.A, b.s.mask, p.A, p.mask_vecw, gc.lane);
+        }
+        const unsigned st = b.ror(b.status);
+        if (gc.lane == 0) p.pool_status[env] = st;
+        __threadfence();   // the board must be visible before the entry is declared valid
+        b.sync();
+        if (gc.lane == 0) p.pool_episode[env] = ep;
+        b.sync();
     }
-    const unsigned st = b.ror(b.status);
-    if (gc.lane == 0) p.pool_status[gc.env] = st;
-    __threadfence();   // the board must be visible before the entry is declared valid
-    b.sync();
-    if (gc.lane == 0) p.pool_episode[gc.env] = ep;
 }
 
 // _get_effective_actions for every env from its current board (ref tile_match_env.py:118-124)
