@@ -37,6 +37,9 @@ P = ROWS * COLS
 A = 2 * P - ROWS - COLS
 # algorithmic bytes per env-step = 4P + 48 + A = 628 B for 10x10 (int8 planes in+out, scalars, mask)
 BYTES_PER_STEP = 4 * P + 48 + A
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch (ncu --set full, profiles/r01_k_step_ncu_raw.txt):
+# 13.6 MB read + ~0 written (no-op steps never load the board; writes stay in the 126 MB L2 within a launch)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.65e6
 METRIC = "env-steps/sec (full cascade, bit-exact)"
 UNIT = "env-steps/s"
 
@@ -257,7 +260,7 @@ def main():
                     "returns": "board,reward,terminated,mask,num_moves_left to pinned host memory, stream synchronised per step"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "tmg::k_step<16>",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "tmg::k_step<16,10,10>",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n_local,
                          "note": "integer/divergence-bound kernel: the HBM fraction is low by construction, see DESIGN.md"},
             "clocks": clocks,

@@ -369,3 +369,38 @@ def test_reference_known_answers_on_device():
                "get_colour_lines", "is_move_effective"):
         assert done.get(fn, 0) > 0, (fn, done)
     print("device KAT replays:", done)
+
+
+def test_32x32_seven_colours_injected_boards():
+    """BASELINE config 5: generate_board never terminates for 32x32 / 7 colours in the reference, so both
+    sides start from injected line-free boards; long cascades, divergence-heavy."""
+    torch = _torch()
+    N, R, Cc, K, moves = 192, 32, 32, 7, 12
+    rng = np.random.default_rng(77)
+
+    def no_line_board():
+        b = np.zeros((R, Cc), dtype=np.int8)
+        for r in range(R):
+            for c in range(Cc):
+                while True:
+                    k = int(rng.integers(1, K + 1))
+                    if c >= 2 and b[r, c - 1] == k and b[r, c - 2] == k:
+                        continue
+                    if r >= 2 and b[r - 1, c] == k and b[r - 2, c] == k:
+                        continue
+                    b[r, c] = k
+                    break
+        return np.stack([b, np.ones_like(b)])
+
+    boards = np.stack([no_line_board() for _ in range(N)]).astype(np.int8)
+    g = GpuAdapter(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=12, autoreset="disabled"))
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=12, autoreset="disabled", num_threads=8)
+    g.reset(init_boards=boards); o.reset(init_boards=boards)
+    assert_same(g, o, "inject")
+    for t in range(moves):
+        m = o.mask.astype(np.float64) + 1e-9
+        u = rng.random((N, 1)) * m.sum(axis=1, keepdims=True)
+        a = (np.cumsum(m, axis=1) < u).sum(axis=1).clip(0, o.A - 1).astype(np.int32)
+        g.step(a); o.step(a)
+        assert_same(g, o, f"step {t}")
+    assert int(o.status.sum()) == 0
