@@ -177,6 +177,7 @@ typedef struct tmg_host_io {
     int32_t *reward;                 /* out [N] or NULL */
     uint8_t *terminated;             /* out [N] or NULL */
     uint8_t *mask;                   /* out [N][A] or NULL */
+    uint8_t *mask_bits;              /* out [N][(A+7)/8] or NULL: the same mask, bit j of byte b = action 8b+j (2.3x fewer PCIe bytes) */
     int32_t *num_moves_left;         /* out [N] or NULL */
     uint8_t *is_combination_match;   /* out [N] or NULL */
     int32_t *num_new_specials;       /* out [N] or NULL */

@@ -236,6 +236,14 @@ def test_host_buffer_path_matches_device_path():
         assert np.array_equal(out["mask"].numpy(), o.mask)
         assert np.array_equal(out["num_moves_left"].numpy(), o.num_moves_left)
     assert hs.h2d_bytes == 4 * N and hs.d2h_bytes == N * (200 + 4 + 1 + 180 + 4 + 4)
+    # bit-packed mask form of the same call
+    hb = HostStepper(env, outputs=("reward", "mask_bits"))
+    for t in range(5):
+        a = rng.integers(0, o.A, size=N).astype(np.int32)
+        out = hb.step(a); o.step(a)
+        bits = np.unpackbits(out["mask_bits"].numpy(), axis=1, bitorder="little")[:, :o.A]
+        assert np.array_equal(bits, o.mask) and np.array_equal(out["reward"].numpy(), o.reward)
+    assert hb.effective_actions(3) == np.flatnonzero(o.mask[3]).tolist()
 
 
 def test_reset_with_seed_and_partial_reset():

@@ -48,7 +48,7 @@ class Buffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BUFFER_FIELDS]
 
 
-HOST_IO_FIELDS = ["actions", "board", "reward", "terminated", "mask", "num_moves_left", "is_combination_match",
+HOST_IO_FIELDS = ["actions", "board", "reward", "terminated", "mask", "mask_bits", "num_moves_left", "is_combination_match",
                   "num_new_specials", "num_specials_activated", "shuffled", "status"]
 
 

@@ -18,6 +18,7 @@ struct tmg_env {
     int L;          // lanes per board: 8, 16 or 32
     int planes;     // one-hot planes
     int32_t* actions_dev;  // staging for tmg_step_host
+    uint8_t* mask_bits_dev;
     void* base;     // one allocation backs every buffer
     size_t bytes;
     // board pool: k_pregen runs on a side stream so that generate_board stays off the step path
@@ -210,7 +211,8 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_mask = take((size_t)N * p.A), o_left = take((size_t)N * 4), o_stat = take((size_t)N * 4),
                  o_actions = take((size_t)N * 4), o_ep = take((size_t)N * 4), o_pool_ep = take((size_t)N * 4),
                  o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
-                 o_pool_status = take((size_t)N * 4), o_pool_req = take((size_t)N * 4);
+                 o_pool_status = take((size_t)N * 4), o_pool_req = take((size_t)N * 4),
+                 o_mask_bits = take((size_t)N * ((p.A + 7) / 8));
     e->bytes = off;
     if (cudaMalloc(&e->base, e->bytes) != cudaSuccess) { cudaGetLastError(); delete e; return TMG_ERR_OOM; }
     if (cudaMemset(e->base, 0, e->bytes) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
@@ -235,6 +237,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.pool_mask = reinterpret_cast<uint8_t*>(b + o_pool_mask);
     p.pool_status = reinterpret_cast<uint32_t*>(b + o_pool_status);
     p.pool_req = reinterpret_cast<int32_t*>(b + o_pool_req);
+    e->mask_bits_dev = reinterpret_cast<uint8_t*>(b + o_mask_bits);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
     {
@@ -409,6 +412,13 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     back(io->reward, p.reward, N * 4);
     back(io->terminated, p.terminated, N);
     back(io->mask, p.mask, N * p.A);
+    if (io->mask_bits) {
+        const int bpe = (p.A + 7) / 8;
+        const long long total = (long long)N * bpe;
+        k_pack_mask<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.mask, e->mask_bits_dev, (int)N, p.A, bpe);
+        ok &= cudaGetLastError() == cudaSuccess;
+        back(io->mask_bits, e->mask_bits_dev, (size_t)total);
+    }
     back(io->num_moves_left, p.moves_left, N * 4);
     back(io->is_combination_match, p.is_comb, N);
     back(io->num_new_specials, p.new_specials, N * 4);

@@ -1683,6 +1683,20 @@ template <typename OUT> __global__ void __launch_bounds__(256) k_onehot(const Pa
     }
 }
 
+// legal-move mask as bits for the host-buffer path: out[env][b] bit j = mask[env][8b + j]  (one thread per output byte)
+__global__ void __launch_bounds__(256) k_pack_mask(const uint8_t* __restrict__ mask, uint8_t* __restrict__ out, int n_envs, int A,
+                                                   int bytes_per_env) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_envs * bytes_per_env) return;
+    const int env = (int)(i / bytes_per_env), b = (int)(i - (long long)env * bytes_per_env);
+    const uint8_t* m = mask + (size_t)env * A + 8 * b;
+    unsigned v = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (8 * b + j < A) v |= (unsigned)(m[j] != 0) << j;
+    out[i] = (uint8_t)v;
+}
+
 __global__ void k_clear_status(uint32_t* st, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) st[i] = 0u;

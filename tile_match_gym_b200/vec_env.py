@@ -311,7 +311,8 @@ class HostStepper:
         self.env = env
         N, R, Cc, A = env.num_envs, env.num_rows, env.num_cols, env.num_actions
         shapes = {"actions": ((N,), torch.int32), "board": ((N, 2, R, Cc), torch.int8), "reward": ((N,), torch.int32),
-                  "terminated": ((N,), torch.uint8), "mask": ((N, A), torch.uint8), "num_moves_left": ((N,), torch.int32),
+                  "terminated": ((N,), torch.uint8), "mask": ((N, A), torch.uint8),
+                  "mask_bits": ((N, (A + 7) // 8), torch.uint8), "num_moves_left": ((N,), torch.int32),
                   "is_combination_match": ((N,), torch.uint8), "num_new_specials": ((N,), torch.int32),
                   "num_specials_activated": ((N,), torch.int32), "shuffled": ((N,), torch.uint8),
                   "status": ((N,), torch.int32)}
@@ -324,6 +325,13 @@ class HostStepper:
             setattr(self.io, name, t.data_ptr())
         self.h2d_bytes = self.host["actions"].numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for n, t in self.host.items() if n != "actions")
+
+    def effective_actions(self, i: int):
+        """The reference's info["effective_actions"] list of env i from whichever mask form was copied back."""
+        if "mask" in self.host:
+            return np.flatnonzero(self.host["mask"][i].numpy()).tolist()
+        bits = np.unpackbits(self.host["mask_bits"][i].numpy(), bitorder="little")[:self.env.num_actions]
+        return np.flatnonzero(bits).tolist()
 
     def step(self, actions=None):
         """actions: optional array-like copied into the pinned staging buffer first (int32, (N,))."""
