@@ -76,7 +76,7 @@ static void trampoline() {
 static void run_group(int L, int first_tid, void (*fn)()) {
     entry_fn = fn;
     group_lanes = L;
-    group_shift = (first_tid & 31) & ~(L - 1);
+    group_shift = first_tid & 31;   // groups need not be a power of two wide (10-lane groups: 0, 10, 20)
     expect_mask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << group_shift;
     alive = L; arrived = 0;
     memset(ncoll, 0, sizeof(ncoll));
@@ -136,7 +136,7 @@ template <int L> static void launch(void (*fn)(), int n) {
     emu::grid_dim = emu::Dim{(unsigned)grid, 1, 1};
     for (int b = 0; b < grid; ++b) {
         emu::block_idx = emu::Dim{(unsigned)b, 0, 0};
-        for (int g = 0; g < gpb; ++g) emu::run_group(L, g * L, fn);
+        for (int g = 0; g < gpb; ++g) emu::run_group(L, (g / Cfg<L>::GPW) * 32 + (g % Cfg<L>::GPW) * L, fn);
     }
 }
 
@@ -174,7 +174,10 @@ void* emu_create(const emu_config* c) {
     p.max_iters = c->max_reset_iters > 0 ? c->max_reset_iters : 16384;
     p.key0 = (uint32_t)c->seed; p.key1 = (uint32_t)(c->seed >> 32); p.env_id_offset = c->env_id_offset;
     p.board_vecw = vec_width((size_t)2 * p.P); p.mask_vecw = vec_width((size_t)p.A); p.init_vecw = 1;
-    e->L = (p.C <= 8 && p.R <= 16) ? 8 : ((p.C <= 16 && p.R <= 16) ? 16 : 32);
+    // 10x10 / 9x9 run the fixed-shape 16-lane kernels (as the library does); other 9/10-column shapes keep the 10-lane
+    // groups covered in the emulator
+    const bool fixed = (p.R == 10 && p.C == 10) || (p.R == 9 && p.C == 9);
+    e->L = (p.R > 16) ? 32 : (p.C <= 8 ? 8 : ((p.C <= 10 && !fixed) ? 10 : (p.C <= 16 ? 16 : 32)));
     const size_t N = (size_t)p.N;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
@@ -209,6 +212,7 @@ void emu_set_injected_draws(void* h, const uint8_t* d, int64_t len) { ((EmuEnv*)
 #define DISPATCH(FN)                                   \
     switch (e->L) {                                    \
         case 8: launch<8>(FN<8>, e->p.N); break;       \
+        case 10: launch<10>(FN<10>, e->p.N); break;    \
         case 16: launch<16>(FN<16>, e->p.N); break;    \
         default: launch<32>(FN<32>, e->p.N); break;    \
     }

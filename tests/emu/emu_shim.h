@@ -65,20 +65,20 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) out |= (unsigned)(v[i] & 1) << i;
     return out;
 }
-template <typename T> static inline T __shfl_sync(unsigned mask, T val, int src, int width) {
+template <typename T> static inline T __shfl_sync(unsigned mask, T val, int src, int width = 32) {
     const uint64_t* v = emu::gather((uint64_t)(uint32_t)val, mask);
     const int me = emu::cur->lane_in_warp;
     const int base = me & ~(width - 1);
     return (T)(uint32_t)v[base + (src & (width - 1))];
 }
-template <typename T> static inline T __shfl_down_sync(unsigned mask, T val, int d, int width) {
+template <typename T> static inline T __shfl_down_sync(unsigned mask, T val, int d, int width = 32) {
     const uint64_t* v = emu::gather((uint64_t)(uint32_t)val, mask);
     const int me = emu::cur->lane_in_warp;
     const int base = me & ~(width - 1);
     const int idx = (me - base) + d;
     return (T)(uint32_t)v[idx < width ? base + idx : me];
 }
-template <typename T> static inline T __shfl_up_sync(unsigned mask, T val, int d, int width) {
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T val, int d, int width = 32) {
     const uint64_t* v = emu::gather((uint64_t)(uint32_t)val, mask);
     const int me = emu::cur->lane_in_warp;
     const int base = me & ~(width - 1);

@@ -15,7 +15,7 @@ using namespace tmg;
 struct tmg_env {
     tmg_config cfg;
     Params p;
-    int L;          // lanes per board: 8, 16 or 32
+    int L;          // lanes per board: 8, 10, 16 or 32
     int planes;     // one-hot planes
     int32_t* actions_dev;  // staging for tmg_step_host
     uint8_t* mask_bits_dev;
@@ -56,9 +56,10 @@ template <int L_, int R_, int C_> struct Shape { static constexpr int L = L_, R 
 template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
     const int R = e->p.R, C = e->p.C;
     static const bool generic_only = getenv("TMG_B200_GENERIC_SHAPES") != nullptr;   // diagnostics: skip the fixed-shape kernels
-    if (generic_only) {
+    if (generic_only || e->L == 10) {
         switch (e->L) {
             case 8: return f(Shape<8, 0, 0>());
+            case 10: return f(Shape<10, 0, 0>());
             case 16: return f(Shape<16, 0, 0>());
             default: return f(Shape<32, 0, 0>());
         }
@@ -68,6 +69,7 @@ template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
     if (R == 32 && C == 32) return f(Shape<32, 32, 32>());
     switch (e->L) {
         case 8: return f(Shape<8, 0, 0>());
+        case 10: return f(Shape<10, 0, 0>());
         case 16: return f(Shape<16, 0, 0>());
         default: return f(Shape<32, 0, 0>());
     }
@@ -75,6 +77,7 @@ template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
 template <typename F> int launch_by_lanes(const tmg_env* e, F&& f) {
     switch (e->L) {
         case 8: return f(std::integral_constant<int, 8>());
+        case 10: return f(std::integral_constant<int, 10>());
         case 16: return f(std::integral_constant<int, 16>());
         default: return f(std::integral_constant<int, 32>());
     }
@@ -184,7 +187,11 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     tmg_env* e = new (std::nothrow) tmg_env();
     if (!e) return TMG_ERR_OOM;
     e->cfg = *cfg;
-    e->L = (C <= 8 && R <= 16) ? 8 : ((C <= 16 && R <= 16) ? 16 : 32);
+    // lanes per board.  10-lane groups (three 9/10-column boards per warp) are supported by the kernels but measured no
+    // faster than 16-lane groups on B200: groups of a warp diverge, so a warp instruction serves one group either way,
+    // and the spare lanes of a 16-lane group compute Philox blocks.  TMG_B200_LANES10=1 selects them for experiments.
+    static const bool lanes10 = getenv("TMG_B200_LANES10") != nullptr;
+    e->L = (R > 16) ? 32 : (C <= 8 ? 8 : ((C <= 10 && lanes10) ? 10 : (C <= 16 ? 16 : 32)));
     e->planes = tmg_onehot_planes(K, cfg->specials);
     Params& p = e->p;
     memset(&p, 0, sizeof(p));

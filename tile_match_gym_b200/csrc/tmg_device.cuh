@@ -90,13 +90,14 @@ struct Params {
 template <int L> struct Cfg {
     static constexpr int MAXR = (L == 32) ? 32 : 16;
     static constexpr int MAXP = MAXR * L;
-    static constexpr int ML = 2 * L;                      // line-table capacity per cascade round
+    static constexpr int ML = (2 * L > 32) ? 2 * L : 32;  // line-table capacity per cascade round
     static constexpr int MLEN = (L > MAXR) ? L : MAXR;    // longest straight line
-    static constexpr int DFS = 4 * L;                     // activation stack depth
+    static constexpr int DFS = (4 * L > 64) ? 4 * L : 64; // activation stack depth
     static constexpr int NW = 4 * (L - 1);                // stream words produced per Philox pass
     static constexpr unsigned LMASK = (L == 32) ? 0xffffffffu : ((1u << (L & 31)) - 1u);
     static constexpr int THREADS = 128;
-    static constexpr int GPB = THREADS / L;               // groups (boards) per block
+    static constexpr int GPW = 32 / L;                    // groups per warp: 4, 3 (L = 10, two lanes idle), 2 or 1
+    static constexpr int GPB = (THREADS / 32) * GPW;      // groups (boards) per block
 };
 
 template <int L> struct __align__(16) GroupSmem {
@@ -282,7 +283,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // ---- group collectives ---------------------------------------------------------------------------
     __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
     __device__ __forceinline__ void sync(TMG_SITE_P0) const { TMG_SITE_SET __syncwarp(gmask); }
-    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, src, L); }
+    // groups need not be a power of two wide (10-lane groups: three 10-column boards per warp), so shuffles address
+    // absolute lanes of the warp
+    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, gshift + src); }
     __device__ __forceinline__ int radd(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_add_sync(gmask, v); }
     __device__ __forceinline__ int rmax(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_max_sync(gmask, v); }
     __device__ __forceinline__ int rmin(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_min_sync(gmask, v); }
@@ -291,12 +294,12 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // neighbour-lane bitboards: value of lane+d / lane-d, 0 outside [0,L)
     __device__ __forceinline__ unsigned from_right(unsigned v, int d TMG_SITE_P) const {
         TMG_SITE_SET
-        const unsigned r = __shfl_down_sync(gmask, v, d, L);
+        const unsigned r = __shfl_down_sync(gmask, v, d);
         return (lane + d < L) ? r : 0u;
     }
     __device__ __forceinline__ unsigned from_left(unsigned v, int d TMG_SITE_P) const {
         TMG_SITE_SET
-        const unsigned r = __shfl_up_sync(gmask, v, d, L);
+        const unsigned r = __shfl_up_sync(gmask, v, d);
         return (lane - d >= 0) ? r : 0u;
     }
     __device__ __forceinline__ unsigned rows_mask() const { return R >= 32 ? 0xffffffffu : ((1u << R) - 1u); }
@@ -1325,12 +1328,16 @@ __device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params*
 template <int L> struct GroupCtx {
     int g, lane, env, gshift;
     unsigned gmask;
+    bool idle;   // lanes of a warp beyond its last whole group (30, 31 when L = 10)
     __device__ GroupCtx() {
-        g = (int)threadIdx.x / L;
-        lane = (int)threadIdx.x % L;
-        env = (int)blockIdx.x * Cfg<L>::GPB + g;
-        gshift = ((int)threadIdx.x & 31) & ~(L - 1);
-        gmask = Cfg<L>::LMASK << gshift;
+        const int warp = (int)threadIdx.x >> 5, wl = (int)threadIdx.x & 31;
+        const int gw = wl / L;
+        idle = gw >= Cfg<L>::GPW;
+        g = warp * Cfg<L>::GPW + gw;
+        lane = wl - gw * L;
+        env = idle ? 0x7fffffff : (int)blockIdx.x * Cfg<L>::GPB + g;
+        gshift = gw * L;
+        gmask = Cfg<L>::LMASK << (gshift & 31);
     }
 };
 
