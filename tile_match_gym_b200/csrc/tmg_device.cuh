@@ -427,6 +427,98 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         dcur += (uint64_t)total;
     }
 
+    // ---- gravity + refill of a cascade round, fused (ref :362-364, :374-376) --------------------------------------
+    // Fixed small shapes: the column is read into registers once, every surviving cell moves down by the number of
+    // empties below it (independent stores, no carried write pointer), the emptied top rows are not zeroed because the
+    // refill overwrites them, and the Philox block each lane will need is computed beside the loads.
+    __device__ __forceinline__ void fall_and_refill(int& elim_add) {
+        if (RT == 0 || RT > 16) {
+            int cnt;
+            const int e = gravity(&cnt);
+            elim_add = cnt;
+            refill(e);
+            return;
+        }
+        constexpr int RR = (RT > 0 && RT <= 16) ? RT : 1;
+        sync();
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        const uint64_t b0 = dcur >> 2;
+        const int off = (int)(dcur & 3ull);
+        if (!p.use_inj) {
+            const uint64_t b = b0 + (uint64_t)lane;
+            philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, 0u, p.key0, p.key1, w);
+        }
+        int x[RR], t[RR];
+        unsigned empt = 0u, tz = 0u;
+        if (lane < C) {
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {
+                x[r] = col[r * C + lane];
+                t[r] = typ[r * C + lane];
+                empt |= (unsigned)(x[r] == 0 && t[r] == 0) << r;
+                tz |= (unsigned)(t[r] == 0) << r;
+            }
+            if (empt) {
+#pragma unroll
+                for (int r = RR - 1; r >= 0; --r) {
+                    const int below = __popc(empt >> (r + 1));     // empties underneath: the cell falls that far
+                    if (!((empt >> r) & 1u) && below) {
+                        col[(r + below) * C + lane] = (int8_t)x[r];
+                        typ[(r + below) * C + lane] = (int8_t)t[r];
+                    }
+                }
+            }
+        }
+        const int e = __popc(empt);
+        elim_add = radd(__popc(tz));                               // ref :362,374: P - count_nonzero(type)
+        unsigned m = ballot(e > 0);
+        if (!m) return;                                            // ref :238: no rng call when nothing is empty
+        if (!p.use_inj) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s.wbuf[4 * lane + i] = w[i];
+        }
+        sync();
+        const unsigned lt = lt_mask();
+        const int avail = 4 * L - off;                             // words of this pass, starting at dcur
+        int base = 0;
+#pragma unroll 1
+        for (int r = 0; m; ++r) {                                  // ref :239-241: k-th draw -> k-th empty cell, row-major
+            if (e > r) {
+                const int rank = base + __popc(m & lt);
+                if (rank < avail) {
+                    col[r * C + lane] = (int8_t)(p.use_inj ? injected_colour(rank)
+                                                           : 1 + (int)__umulhi(s.wbuf[off + rank], (uint32_t)K));
+                    typ[r * C + lane] = 1;
+                }
+            }
+            base += __popc(m);
+            m = ballot(e > r + 1);
+        }
+        const int total = base;
+#pragma unroll 1
+        for (int ps = avail; ps < total; ps += CF::NW) {           // rare: more empties than one pass of words
+            const int nw = min(CF::NW, total - ps);
+            sync();
+            if (!p.use_inj) fill_words(0u, dcur + (uint64_t)ps, nw);
+            int bs = 0;
+#pragma unroll 1
+            for (int r = 0; r < RR; ++r) {
+                const unsigned mm = ballot(e > r);
+                if (e > r) {
+                    const int rank = bs + __popc(mm & lt);
+                    if (rank >= ps && rank < ps + nw) {
+                        col[r * C + lane] = (int8_t)(p.use_inj ? injected_colour(rank)
+                                                               : 1 + (int)__umulhi(s.wbuf[rank - ps], (uint32_t)K));
+                        typ[r * C + lane] = 1;
+                    }
+                }
+                bs += __popc(mm);
+            }
+        }
+        dcur += (uint64_t)total;
+        sync();
+    }
+
     // ---- line detection (ref :149-215) ---------------------------------------------------------------------
     // Per-lane row bitboards of column c: E bit r: colour(r,c)==colour(r,c+1); D bit r: colour(r,c)==colour(r-1,c);
     // T bit r: type(r,c) > 0.  One pass over the column finds every anchored line of the board at once.
@@ -1265,17 +1357,15 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             const SlowOut o = slow_combination<L, RT, CT>(&s, &p, lane, gmask, gshift, env, i1, i2);  // ref :361
             n_new = o.n_new; n_act = o.n_act; status |= o.status;
             int e_cnt;
-            const int e = gravity(&e_cnt);                   // ref :362-363
+            fall_and_refill(e_cnt);                          // ref :362-364
             elim += e_cnt;
-            refill(e);                                       // ref :364
         }
 #pragma unroll 1
         for (;;) {                                           // ref :367-376
             if (resolve_round() == 0) break;
             int e_cnt;
-            const int e = gravity(&e_cnt);
+            fall_and_refill(e_cnt);                          // ref :374-376
             elim += e_cnt;
-            refill(e);
         }
         elim_out = elim + n_new;                             // ref :378 (counters are uniform across lanes)
     }
