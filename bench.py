@@ -221,8 +221,8 @@ def main():
     status_bad = int((env.status != 0).sum().item())
 
     # ---- end-to-end timing through the host-buffer call (pinned host memory in and out) -----------------------
-    def time_host_path(outputs):
-        hs = HostStepper(env, outputs=outputs)
+    def time_host_path(outputs, mirror=False):
+        hs = HostStepper(env, outputs=outputs, mirror=mirror)
         for i in range(3):
             hs.io.actions = host_actions[i % n_act].data_ptr()
             hs.step()
@@ -234,22 +234,36 @@ def main():
             hs.step()
         e1.record(stream)
         barrier()
-        return hs, e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1)
+        if mirror:   # bytes the kernel wrote over PCIe: counted on one further, untimed episode
+            changed = 0
+            for i in range(num_moves if num_moves < 1000 else 30):
+                hs.io.actions = host_actions[i % n_act].data_ptr()
+                out = hs.step()
+                changed += int(((out["reward"] > 0) | (out["terminated"] != 0)).sum())
+            hs.avg_changed = changed / (num_moves if num_moves < 1000 else 30)
+            hs.d2h_bytes = int(hs.d2h_bytes_fixed + hs.avg_changed * hs.d2h_bytes_per_changed_env)
+            hs.close()
+        return hs, ms
 
     host_actions = [a.cpu().pin_memory() for a in actions]
     e2e_steps = 3 if args.skip_e2e else max(10, min(args.steps, 60))
     # the full result of TileMatchEnv.step for every env: board, reward, terminated, legal-move mask, num_moves_left.
     # Headline form: mask as bits (same information as the reference's effective_actions list, 23 B instead of 180 B
     # per env over PCIe); the byte-mask form is reported beside it.
-    hs, e2e_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"))
+    # Headline form: board and bit-packed mask bound as the host mirror (tmg_host_bind) -- the step kernel writes the
+    # entries of the envs it changed straight into the pinned arrays, the scalars come back by copy.  The full-copy
+    # forms (every array copied after every step) are reported beside it.
+    hs, e2e_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"), mirror=True)
+    hs_full, e2e_full_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"))
     hs_bytes, e2e_bytes_ms = time_host_path(("board", "reward", "terminated", "mask", "num_moves_left"))
     clocks = sampler.summary()
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms, e2e_bytes_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, e2e_bytes_ms = t.tolist()
+        total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms = t.tolist()
         bad = torch.tensor([status_bad], device=dev); dist.all_reduce(bad); status_bad = int(bad.item())
     n_global = n_local * world
     value = n_global * args.steps / (total_ms * 1e-3)
@@ -264,13 +278,18 @@ def main():
             "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes * world,
                     "d2h_bytes_per_step": hs.d2h_bytes * world, "steps": e2e_steps,
-                    "returns": "board,reward,terminated,mask(bit-packed),num_moves_left to pinned host memory, stream "
-                               "synchronised per step",
-                    "with_byte_mask": {"value": n_global * e2e_steps / (e2e_bytes_ms * 1e-3),
-                                       "d2h_bytes_per_step": hs_bytes.d2h_bytes * world}},
-            "gpu_launches": args.steps,
+                    "returns": "board,reward,terminated,mask(bit-packed),num_moves_left in pinned host memory, complete and "
+                               "current after every step, stream synchronised per step; board and mask are a host mirror "
+                               "(tmg_host_bind) that the step kernel updates in place for the envs it changed "
+                               f"({hs.avg_changed / n_local:.3f} of the envs per step), scalars are copied in full",
+                    "full_copy_every_step": {"value": n_global * e2e_steps / (e2e_full_ms * 1e-3),
+                                             "d2h_bytes_per_step": hs_full.d2h_bytes * world},
+                    "full_copy_byte_mask": {"value": n_global * e2e_steps / (e2e_bytes_ms * 1e-3),
+                                            "d2h_bytes_per_step": hs_bytes.d2h_bytes * world}},
+            # k_gate + k_work per step, plus one k_pregen per step on a side stream
+            "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "tmg::k_step<16,10,10>",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "tmg::k_gate + tmg::k_work<16,10,10> (one tmg_step)",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n_local,
                          "note": "integer/divergence-bound kernel: the HBM fraction is low by construction, see DESIGN.md"},
             "clocks": clocks,

@@ -47,6 +47,7 @@ def lib():
         L.emu_create.argtypes = [C.POINTER(_Cfg)]
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_get_buffers.argtypes = [C.c_void_p, C.POINTER(_Bufs)]
+        L.emu_host_bind.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_set_injected_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.emu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_void_p]
@@ -93,6 +94,14 @@ class EmuVecEnv:
         d = np.ascontiguousarray(draws, dtype=np.uint8)
         self._keep.append(d)
         self.L.emu_set_injected_draws(self.h, _ptr(d), d.shape[1])
+
+    def host_bind(self):
+        """Mirror arrays (plain memory here) initialised from the current state, as tmg_host_bind does."""
+        bpe = (self.A + 7) // 8
+        self.h_board = self.board.copy()
+        self.h_mask = self.mask.copy()
+        self.h_mask_bits = np.packbits(self.mask, axis=1, bitorder="little")[:, :bpe].copy()
+        self.L.emu_host_bind(self.h, _ptr(self.h_board), _ptr(self.h_mask), _ptr(self.h_mask_bits))
 
     def reset(self, reset_mask=None, init_boards=None):
         m = None if reset_mask is None else np.ascontiguousarray(reset_mask, dtype=np.uint8)

@@ -115,10 +115,21 @@ template <int L> static void e_reset() {
     else k_reset<L, 0, 0>(g_params);
 }
 template <int L> static void e_step() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_step<16, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_step<16, 9, 9>(g_params);
-    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_step<32, 32, 32>(g_params);
-    else k_step<L, 0, 0>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_work<16, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_work<16, 9, 9>(g_params);
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_work<32, 32, 32>(g_params);
+    else k_work<L, 0, 0>(g_params);
+}
+static void e_gate() { k_gate(g_params); }
+// one thread per env, whole warps (k_gate)
+static void launch_threads(void (*fn)(), int n) {
+    const int grid = (n + 127) / 128;
+    emu::block_dim = emu::Dim{128u, 1, 1};
+    emu::grid_dim = emu::Dim{(unsigned)grid, 1, 1};
+    for (int b = 0; b < grid; ++b) {
+        emu::block_idx = emu::Dim{(unsigned)b, 0, 0};
+        for (int w = 0; w < 4; ++w) emu::run_group(32, w * 32, fn);
+    }
 }
 template <int L> static void e_pregen() {
     if (g_params.R == 10 && g_params.C == 10 && L == 16) k_pregen<16, 10, 10>(g_params);
@@ -143,7 +154,7 @@ template <int L> static void launch(void (*fn)(), int n) {
 struct EmuEnv {
     Params p;
     int L;
-    int tag = 0;
+    int tag = 0, seq = 0;
     std::vector<char> mem;
 };
 
@@ -181,9 +192,11 @@ void* emu_create(const emu_config* c) {
     const size_t N = (size_t)p.N;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
-    size_t o[19] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
+    size_t cap = 1;
+    while (cap < N) cap <<= 1;
+    size_t o[21] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
                     take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4), take(N * 4), take(N * 4),
-                    take(N * 2 * p.P), take(N * p.A), take(N * 4), take(N * 4)};
+                    take(N * 2 * p.P), take(N * p.A), take(N * 4), take(CTL_WORDS * 4), take(N * 8), take(cap * 4)};
     e->mem.assign(off + 256, 0);
     char* b = e->mem.data();
     b += (256 - ((uintptr_t)b & 255)) & 255;
@@ -194,8 +207,9 @@ void* emu_create(const emu_config* c) {
     p.status = (uint32_t*)(b + o[12]);
     p.episode = (int32_t*)(b + o[13]); p.pool_episode = (int32_t*)(b + o[14]);
     p.pool_board = (int8_t*)(b + o[15]); p.pool_mask = (uint8_t*)(b + o[16]); p.pool_status = (uint32_t*)(b + o[17]);
-    p.pool_req = (int32_t*)(b + o[18]);
-    for (size_t i = 0; i < N; ++i) p.pool_req[i] = -1;
+    p.ctl = (uint32_t*)(b + o[18]); p.wl_items = (uint2*)(b + o[19]); p.req_mask = (uint32_t)(cap - 1);
+    const bool pregen = !p.use_inj && !(p.flags & 2u) && p.autoreset != 0;
+    p.req_ring = pregen ? (int32_t*)(b + o[20]) : nullptr;
     for (size_t i = 0; i < N; ++i) { p.timer[i] = -1; p.episode[i] = -1; p.pool_episode[i] = (int32_t)0x80808080; }
     return e;
 }
@@ -206,6 +220,10 @@ void emu_get_buffers(void* h, emu_buffers* o) {
     o->reward = p.reward; o->terminated = p.terminated; o->is_combination_match = p.is_comb;
     o->num_new_specials = p.new_specials; o->num_specials_activated = p.activated; o->shuffled = p.shuffled;
     o->mask = p.mask; o->num_moves_left = p.moves_left; o->status = p.status; o->episode = p.episode;
+}
+void emu_host_bind(void* h, int8_t* board, uint8_t* mask, uint8_t* mask_bits) {   // the mirror is ordinary memory here
+    Params& p = ((EmuEnv*)h)->p;
+    p.h_board = board; p.h_mask = mask; p.h_mask_bits = mask_bits;
 }
 void emu_set_injected_draws(void* h, const uint8_t* d, int64_t len) { ((EmuEnv*)h)->p.inj = d; ((EmuEnv*)h)->p.inj_len = len; }
 
@@ -225,7 +243,8 @@ void emu_reset(void* h, const uint8_t* reset_mask, const int8_t* init_boards) {
 }
 void emu_step(void* h, const int32_t* actions) {
     EmuEnv* e = (EmuEnv*)h;
-    g_params = e->p; g_params.actions = actions; g_params.pool_tag = e->tag;
+    g_params = e->p; g_params.actions = actions; g_params.pool_tag = e->tag; g_params.seq = e->seq++ & 1;
+    launch_threads(e_gate, e->p.N);
     DISPATCH(e_step)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) { g_params = e->p; g_params.pool_tag = e->tag++; DISPATCH(e_pregen) }
 }

@@ -42,7 +42,7 @@ def test_sass_is_sm_100a_and_has_the_kernels():
     out = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
     res = subprocess.run(["cuobjdump", "-res-usage", path], capture_output=True, text=True).stdout
-    for k in ("k_step", "k_reset", "k_mask", "k_onehot", "k_debug"):
+    for k in ("k_gate", "k_work", "k_pregen", "k_reset", "k_mask", "k_onehot", "k_debug"):
         assert k in res
 
 

@@ -45,6 +45,23 @@ def test_emulated_batch_vs_oracle(cfg):
             assert np.array_equal(getattr(e, f), getattr(o, f)), (t, f)
 
 
+@pytest.mark.parametrize("R,C,K,moves,autoreset", [(10, 10, 4, 6, "same_step"), (5, 7, 3, 4, "disabled"), (9, 9, 6, 5, "next_step")])
+def test_emulated_host_mirror_tracks_device_state(R, C, K, moves, autoreset):
+    """tmg_host_bind's write-through: after every step the mirror arrays equal board / mask / packed mask."""
+    N = 24
+    e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=5, autoreset=autoreset)
+    e.reset()
+    e.host_bind()
+    rng = np.random.default_rng(3)
+    for t in range(3 * moves):
+        if autoreset == "disabled" and t and t % moves == 0:
+            e.reset(); e.host_bind()
+        e.step(rng.integers(0, e.A, N).astype(np.int32))
+        assert np.array_equal(e.h_board, e.board), t
+        assert np.array_equal(e.h_mask, e.mask), t
+        assert np.array_equal(e.h_mask_bits, np.packbits(e.mask, axis=1, bitorder="little")), t
+
+
 # ----------------------------------------------------------------------------------------------
 # primitive-level differential fuzz: one engine primitive on random boards (dense specials, few colours so that
 # crossings / long lines / chains are common), device code (emulated) vs oracle, for several special subsets

@@ -246,6 +246,36 @@ def test_host_buffer_path_matches_device_path():
     assert hb.effective_actions(3) == np.flatnonzero(o.mask[3]).tolist()
 
 
+@pytest.mark.parametrize("autoreset,R,Cc,K", [("same_step", 10, 10, 4), ("next_step", 9, 9, 6), ("disabled", 7, 12, 5)])
+def test_host_mirror_write_through_matches_oracle(autoreset, R, Cc, K):
+    """tmg_host_bind: the step kernel updates pinned host arrays in place for the envs it changes; after every call
+    the arrays must hold the complete current board / mask / packed mask."""
+    from tile_match_gym_b200 import HostStepper
+    N, moves = 2500, 7
+    env = make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=8, autoreset=autoreset)
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=8, autoreset=autoreset, num_threads=8)
+    env.reset(); o.reset()
+    hs = HostStepper(env, outputs=("board", "reward", "terminated", "mask", "mask_bits", "num_moves_left"), mirror=True)
+    _torch().cuda.synchronize()
+    assert np.array_equal(hs.host["board"].numpy(), o.board) and np.array_equal(hs.host["mask"].numpy(), o.mask)
+    rng = np.random.default_rng(15)
+    for t in range(3 * moves + 2):
+        if autoreset == "disabled" and t and t % moves == 0:
+            env.reset(); o.reset()          # tmg_reset re-copies the bound arrays in full
+        a = rng.integers(0, o.A, size=N).astype(np.int32)
+        out = hs.step(a); o.step(a)
+        assert np.array_equal(out["board"].numpy(), o.board), t
+        assert np.array_equal(out["mask"].numpy(), o.mask), t
+        assert np.array_equal(np.unpackbits(out["mask_bits"].numpy(), axis=1, bitorder="little")[:, :o.A], o.mask), t
+        assert np.array_equal(out["reward"].numpy(), o.reward) and np.array_equal(out["terminated"].numpy(), o.terminated)
+        assert np.array_equal(out["num_moves_left"].numpy(), o.num_moves_left)
+    hs.close()
+    # pageable memory is refused, not silently staged
+    import ctypes as C
+    bad = np.zeros((N, 2, R, Cc), np.int8)
+    assert env._lib.tmg_host_bind(env._h, C.c_void_p(bad.ctypes.data), None, None, env._stream()) != 0
+
+
 def test_reset_with_seed_and_partial_reset():
     torch = _torch()
     N, R, Cc, K, moves = 600, 6, 6, 4, 50

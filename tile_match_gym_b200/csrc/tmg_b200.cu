@@ -23,12 +23,17 @@ struct tmg_env {
     size_t bytes;
     // board pool: k_pregen runs on a side stream so that generate_board stays off the step path
     static constexpr int SIDE = 4;    // independent refill launches overlap each other and the steps
-    static constexpr int RING = 32;   // multiple of SIDE: an event slot always belongs to the same side stream
+    static constexpr int RING = tmg::PG_RING;   // multiple of SIDE: an event slot always belongs to the same side stream
     cudaStream_t side[SIDE];
     cudaEvent_t ev_step, ev_pregen[RING];
     long long pregen_count;   // number of k_pregen launches so far
-    int pregen_grid_cap;      // blocks per k_pregen launch: about half of the resident-block slots of the device
+    long long step_count;     // number of tmg_step calls so far (parity selects the work-list counters)
+    int persistent_blocks;    // resident-block slots of the device for k_work / k_pregen (persistent groups)
+    int pregen_grid_cap;      // diagnostics: cap on the blocks of a k_pregen launch
     bool pregen;              // pool in use (philox refill, not disabled by flag)
+    // host mirror (tmg_host_bind): the caller's page-locked arrays; p.h_* are their device-visible aliases
+    int8_t* hm_board;
+    uint8_t *hm_mask, *hm_mask_bits;
 };
 
 namespace {
@@ -113,9 +118,10 @@ static int launch_pregen(tmg_env* e, cudaStream_t st) {
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
-        const int full = grid_for<L>(p.N);
-        const int cap = e->pregen_grid_cap;
-        k_pregen<L, S::R, S::C><<<full < cap ? full : cap, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), side>>>(p);
+        int grid = grid_for<L>(p.N);
+        if (grid > e->persistent_blocks) grid = e->persistent_blocks;
+        if (grid > e->pregen_grid_cap) grid = e->pregen_grid_cap;
+        k_pregen<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), side>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
@@ -218,8 +224,11 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_mask = take((size_t)N * p.A), o_left = take((size_t)N * 4), o_stat = take((size_t)N * 4),
                  o_actions = take((size_t)N * 4), o_ep = take((size_t)N * 4), o_pool_ep = take((size_t)N * 4),
                  o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
-                 o_pool_status = take((size_t)N * 4), o_pool_req = take((size_t)N * 4),
-                 o_mask_bits = take((size_t)N * ((p.A + 7) / 8));
+                 o_pool_status = take((size_t)N * 4), o_mask_bits = take((size_t)N * ((p.A + 7) / 8)),
+                 o_ctl = take((size_t)CTL_WORDS * 4), o_items = take((size_t)N * sizeof(uint2));
+    size_t req_cap = 1;
+    while (req_cap < (size_t)N) req_cap <<= 1;
+    const size_t o_ring = take(req_cap * 4);
     e->bytes = off;
     if (cudaMalloc(&e->base, e->bytes) != cudaSuccess) { cudaGetLastError(); delete e; return TMG_ERR_OOM; }
     if (cudaMemset(e->base, 0, e->bytes) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
@@ -243,10 +252,20 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.pool_board = reinterpret_cast<int8_t*>(b + o_pool_board);
     p.pool_mask = reinterpret_cast<uint8_t*>(b + o_pool_mask);
     p.pool_status = reinterpret_cast<uint32_t*>(b + o_pool_status);
-    p.pool_req = reinterpret_cast<int32_t*>(b + o_pool_req);
+    p.ctl = reinterpret_cast<uint32_t*>(b + o_ctl);
+    p.wl_items = reinterpret_cast<uint2*>(b + o_items);
+    p.req_mask = (uint32_t)(req_cap - 1);
     e->mask_bits_dev = reinterpret_cast<uint8_t*>(b + o_mask_bits);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
+    e->step_count = 0;
+    e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr;
+    p.req_ring = e->pregen ? reinterpret_cast<int32_t*>(b + o_ring) : nullptr;
+    e->persistent_blocks = prop.multiProcessorCount * TMG_STEP_MIN_BLOCKS;
+    {
+        const char* ppsm = getenv("TMG_B200_BLOCKS_PER_SM");   // tuning knob: persistent blocks per SM
+        if (ppsm && atoi(ppsm) > 0) e->persistent_blocks = prop.multiProcessorCount * atoi(ppsm);
+    }
     {
         // tuning knob: cap the refill kernel to this many blocks per SM.  Measured on B200 (65 536 envs): uncapped is
         // best overall -- a capped refill delays fewer steps but runs longer beside more of them.
@@ -256,8 +275,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     }
     for (int i = 0; i < tmg_env::SIDE; ++i) e->side[i] = nullptr;
     bool ok = cudaMemset(p.episode, 0xff, (size_t)N * 4) == cudaSuccess &&       // -1: no board generated yet
-              cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess &&  // never equal to a real episode
-              cudaMemset(p.pool_req, 0xff, (size_t)N * 4) == cudaSuccess;
+              cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess;    // never equal to a real episode
     if (e->pregen) {
         for (int i = 0; i < tmg_env::SIDE; ++i) ok = ok && cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming) == cudaSuccess;
@@ -303,6 +321,42 @@ int tmg_set_injected_draws(tmg_env* e, const uint8_t* draws_dev, int64_t per_env
     return TMG_OK;
 }
 
+// full copy of the bound mirror arrays (after calls that rewrite boards / masks wholesale)
+static int refresh_mirror(tmg_env* e, cudaStream_t st) {
+    const Params& p = e->p;
+    const size_t N = (size_t)p.N;
+    bool ok = true;
+    if (e->hm_board) ok &= cudaMemcpyAsync(e->hm_board, p.board, N * 2 * p.P, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (e->hm_mask) ok &= cudaMemcpyAsync(e->hm_mask, p.mask, N * p.A, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (e->hm_mask_bits) {
+        const int bpe = (p.A + 7) / 8;
+        const long long total = (long long)N * bpe;
+        k_pack_mask<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.mask, e->mask_bits_dev, (int)N, p.A, bpe);
+        ok &= cudaGetLastError() == cudaSuccess;
+        ok &= cudaMemcpyAsync(e->hm_mask_bits, e->mask_bits_dev, (size_t)total, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    }
+    return ok ? TMG_OK : TMG_ERR_CUDA;
+}
+
+int tmg_host_bind(tmg_env* e, int8_t* board_host, uint8_t* mask_host, uint8_t* mask_bits_host, void* stream) {
+    if (!e) return TMG_ERR_INVALID_ARG;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    void* dev[3] = {nullptr, nullptr, nullptr};
+    void* host[3] = {board_host, mask_host, mask_bits_host};
+    for (int i = 0; i < 3; ++i) {
+        if (!host[i]) continue;
+        if (reinterpret_cast<uintptr_t>(host[i]) % 16 != 0) return TMG_ERR_INVALID_ARG;
+        // page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) memory only: the kernels write it directly
+        if (cudaHostGetDevicePointer(&dev[i], host[i], 0) != cudaSuccess) { cudaGetLastError(); return TMG_ERR_INVALID_ARG; }
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->hm_board = board_host; e->hm_mask = mask_host; e->hm_mask_bits = mask_bits_host;
+    e->p.h_board = static_cast<int8_t*>(dev[0]);
+    e->p.h_mask = static_cast<uint8_t*>(dev[1]);
+    e->p.h_mask_bits = static_cast<uint8_t*>(dev[2]);
+    return refresh_mirror(e, st);
+}
+
 int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boards_dev, void* stream) {
     if (!e) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
@@ -320,6 +374,8 @@ int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boar
         return last_error();
     });
     if (rc != TMG_OK) return rc;
+    const int rc2 = refresh_mirror(e, st);
+    if (rc2 != TMG_OK) return rc2;
     return launch_pregen(e, st);
 }
 
@@ -330,16 +386,21 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
     p.actions = actions_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
+    p.seq = (int)(e->step_count++ & 1);
     if (e->pregen) {
         // An env consumes its pool entry at most once per episode, so only refills tagged num_moves or more launches
         // ago can be needed by this step; everything newer keeps running beside the step kernels.
         const long long W = p.num_moves < 24 ? p.num_moves : 24;   // < RING - SIDE so the event slots are still live
         if (!wait_pregen(e, st, e->pregen_count - W)) return TMG_ERR_CUDA;
     }
+    k_gate<<<(p.N + 127) / 128, 128, 0, st>>>(p);
+    if (last_error() != TMG_OK) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
-        k_step<L, S::R, S::C><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        int grid = grid_for<L>(p.N);
+        if (grid > e->persistent_blocks) grid = e->persistent_blocks;
+        k_work<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
@@ -351,11 +412,12 @@ int tmg_legal_mask(tmg_env* e, void* stream) {
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     const Params p = e->p;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return launch_by_lanes(e, [&](auto lanes) {
+    const int rc = launch_by_lanes(e, [&](auto lanes) {
         constexpr int L = decltype(lanes)::value;
         k_mask<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
+    return rc != TMG_OK ? rc : refresh_mirror(e, st);
 }
 
 static int onehot_launch(tmg_env* e, void* out, bool f32, void* stream) {
@@ -415,11 +477,12 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     auto back = [&](void* dst, const void* src, size_t bytes) {
         if (dst) ok &= cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     };
-    back(io->board, p.board, N * 2 * p.P);
+    // arrays bound as the host mirror were already updated in place by the step kernel
+    if (io->board != e->hm_board) back(io->board, p.board, N * 2 * p.P);
     back(io->reward, p.reward, N * 4);
     back(io->terminated, p.terminated, N);
-    back(io->mask, p.mask, N * p.A);
-    if (io->mask_bits) {
+    if (io->mask != e->hm_mask) back(io->mask, p.mask, N * p.A);
+    if (io->mask_bits && io->mask_bits != e->hm_mask_bits) {
         const int bpe = (p.A + 7) / 8;
         const long long total = (long long)N * bpe;
         k_pack_mask<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.mask, e->mask_bits_dev, (int)N, p.A, bpe);
@@ -450,11 +513,12 @@ int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) 
     p.dbg_args = args_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!join_pregen(e, st)) return TMG_ERR_CUDA;
-    return launch_by_lanes(e, [&](auto lanes) {
+    const int rc = launch_by_lanes(e, [&](auto lanes) {
         constexpr int L = decltype(lanes)::value;
         k_debug<L><<<grid_for<L>(p.N), Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
+    return rc != TMG_OK ? rc : refresh_mirror(e, st);
 }
 
 }  // extern "C"

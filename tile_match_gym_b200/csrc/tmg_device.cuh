@@ -24,14 +24,31 @@
 #define TMG_SITE_P0 int site_ = __builtin_LINE()
 #define TMG_SITE_P , int site_ = __builtin_LINE()
 #define TMG_SITE_SET emu::site_id = site_;
+#define TMG_SITE_HERE emu::site_id = __LINE__;
 #else
 #include <cuda_runtime.h>
 #define TMG_SITE_P0
 #define TMG_SITE_P
 #define TMG_SITE_SET
+#define TMG_SITE_HERE
+#endif
+
+// Code-size knobs.  The step kernel is bound by instruction supply (ncu: stall_no_instruction is the top stall, L1.5
+// hit rate 67 %), but rolling the row loops (-DTMG_UNROLL_ROWS=1 -DTMG_UNROLL_PHILOX=1 -DTMG_FUSED_FALL=0: 15 % less
+// SASS) measured 10 % SLOWER on B200 than the unrolled form: the extra executed instructions cost more than the
+// cache misses they save.
+#ifndef TMG_UNROLL_PHILOX
+#define TMG_UNROLL_PHILOX 10
+#endif
+#ifndef TMG_UNROLL_ROWS
+#define TMG_UNROLL_ROWS 32
+#endif
+#ifndef TMG_FUSED_FALL
+#define TMG_FUSED_FALL 1
 #endif
 
 namespace tmg {
+constexpr int UNROLL_PHILOX = TMG_UNROLL_PHILOX, UNROLL_ROWS = TMG_UNROLL_ROWS;
 
 // ---- status / config constants (values mirror include/tmg_b200.h) ---------------------------------
 enum : uint32_t {
@@ -75,8 +92,18 @@ struct Params {
     uint8_t* pool_mask;      // [N][A]       its legal-move mask
     int32_t* pool_episode;   // [N]          which episode the pool entry belongs to (-1 = none)
     uint32_t* pool_status;   // [N]          status bits raised while generating it (merged when it is consumed)
-    int32_t* pool_req;       // [N]          tag of the k_pregen launch that must refill this env's entry
-    int pool_tag;            // tag handed out by this launch (k_step / k_reset) or served by it (k_pregen)
+    int pool_tag;            // number of the k_pregen launch that serves the requests of this launch (k_gate / k_reset)
+    // scheduling state (device): see Ctl below
+    uint32_t* ctl;           // control words
+    uint2* wl_items;         // [N] work list of the current step: {env, action | flags << 12}
+    int32_t* req_ring;       // [req_mask + 1] envs whose pool entry must be refilled, in request order (NULL: pool not in use)
+    uint32_t req_mask;       // ring capacity - 1 (capacity = power of two >= N)
+    int seq;                 // number of this tmg_step call: its parity selects the work-list counters
+    // host mirror (tmg_host_bind): page-locked host arrays, as device-visible pointers, that the step kernel updates in
+    // place over PCIe for exactly the envs whose board / mask changed (NULL = not bound)
+    int8_t* h_board;         // [N][2][R][C]
+    uint8_t* h_mask;         // [N][A]
+    uint8_t* h_mask_bits;    // [N][(A+7)/8]  bit j of byte b = action 8b + j
     // per-call inputs
     const int32_t* actions;
     const uint8_t* reset_mask;
@@ -86,6 +113,24 @@ struct Params {
     uint32_t* prof;  // optional [N][8]: cycles total, cycles in the general path, cascade rounds, redraw iterations,
                      // then general-path cycles split into scan / line table / classification / resolution (zero before each step)
 };
+
+// Control words.  A step is two launches: k_gate (one thread per env) decides which envs need board work and appends
+// them to the work list; k_work (persistent groups) pops items until the list is empty, so a group that finishes a
+// short item immediately takes the next one and the launch does not wait on whole blocks of idle groups.  Requests
+// for pool refills go to a ring in request order; the launch that issued them records its [start, end) range under
+// its tag so that the k_pregen launch with that tag serves exactly those.
+enum { PG_RING = 32 };       // k_pregen launches whose ranges are kept (host: event ring of the same size)
+enum {
+    CTL_WL_COUNT = 0,        // [2] items appended by k_gate, by step parity
+    CTL_WL_HEAD = 2,         // [2] pop cursor of k_work, by step parity
+    CTL_DONE = 4,            // warps / groups of the running k_gate / k_reset that have finished
+    CTL_REQ_TAIL = 5,        // refill requests appended so far (monotonic, wraps with the ring)
+    CTL_REQ_PREV = 6,        // CTL_REQ_TAIL at the end of the previous requesting launch
+    CTL_PG_RANGE = 8,        // [PG_RING][2] request range served by k_pregen launch `tag`, at tag % PG_RING
+    CTL_PG_HEAD = CTL_PG_RANGE + 2 * PG_RING,   // [PG_RING] pop cursor of that launch
+    CTL_WORDS = CTL_PG_HEAD + PG_RING
+};
+enum : uint32_t { IT_ACTION = 0xfffu, IT_EFF = 1u << 12, IT_REGEN = 1u << 13, IT_ZERO_MASK = 1u << 14, IT_FROM_POOL = 1u << 15 };
 
 template <int L> struct Cfg {
     static constexpr int MAXR = (L == 32) ? 32 : 16;
@@ -121,7 +166,8 @@ template <int L> struct __align__(16) GroupSmem {
 // ---- Philox4x32-10 (Random123) ---------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t out[4]) {
-#pragma unroll
+    // rolled: the instruction caches (L0 ~6 KB, L1.5 32 KB per SM) bound this engine, not the issue rate
+#pragma unroll UNROLL_PHILOX
     for (int i = 0; i < 10; ++i) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -318,6 +364,29 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         copy_bytes<L>(p.mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
     }
     __device__ __forceinline__ void store_zero_mask() { zero_bytes<L>(p.mask + (size_t)env * p.A, p.A, p.mask_vecw, lane); }
+    // host mirror: this env's mask (s.mask, or all zero) as bytes and / or bits, straight into page-locked host memory
+    __device__ __forceinline__ void mirror_mask(bool zero) {
+        if (p.h_mask) {
+            if (zero) zero_bytes<L>(p.h_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
+            else copy_bytes<L>(p.h_mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
+        }
+        if (p.h_mask_bits) {
+            const int bpe = (p.A + 7) >> 3;
+            uint8_t* dst = p.h_mask_bits + (size_t)env * bpe;
+#pragma unroll 1
+            for (int b = lane; b < bpe; b += L) {
+                unsigned v = 0u;
+                if (!zero) {
+                    const uint32_t* m32 = reinterpret_cast<const uint32_t*>(s.mask + 8 * b);
+                    // bytes 0/1 at bits 0,8,16,24 -> 4 adjacent bits: the products land on distinct bit positions
+                    v = ((((m32[0] & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) | (((((m32[1] & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << 4);
+                    const int valid = p.A - 8 * b;
+                    if (valid < 8) v &= (1u << valid) - 1u;
+                }
+                dst[b] = (uint8_t)v;
+            }
+        }
+    }
     __device__ __forceinline__ void load_cursors() { dcur = p.draw_cursor[env]; scur = p.shuffle_cursor[env]; }
     __device__ __forceinline__ void store_cursors() {
         if (lane == 0) { p.draw_cursor[env] = dcur; p.shuffle_cursor[env] = scur; }
@@ -383,6 +452,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         int e = 0, nz = 0;
         if (lane < C) {
             int w = R - 1;
+#pragma unroll UNROLL_ROWS
             for (int r = R - 1; r >= 0; --r) {
                 const int i = r * C + lane;
                 const int x = col[i], t = typ[i];
@@ -432,7 +502,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // empties below it (independent stores, no carried write pointer), the emptied top rows are not zeroed because the
     // refill overwrites them, and the Philox block each lane will need is computed beside the loads.
     __device__ __forceinline__ void fall_and_refill(int& elim_add) {
-        if (RT == 0 || RT > 16) {
+        if (!TMG_FUSED_FALL || RT == 0 || RT > 16) {
             int cnt;
             const int e = gravity(&cnt);
             elim_add = cnt;
@@ -529,7 +599,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         if (lane < C) {
             int prev = -3;
             const bool has_right = lane + 1 < C;
-#pragma unroll
+#pragma unroll UNROLL_ROWS
             for (int r = 0; r < (RT ? RT : R); ++r) {
                 const int i = r * C + lane;
                 const int x = col[i];
@@ -756,9 +826,15 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // activate_special (ref :473-556) as an explicit-stack DFS; all lanes, uniform control flow
     __device__ void activate(int cell0, int t0, bool counted) {
         int sp = 0;
-        enter_activation(cell0, t0, counted, sp);
+        int e_cell = cell0, e_t = t0;
+        bool e_counted = counted;
 #pragma unroll 1
-        while (sp > 0) {
+        for (;;) {
+            enter_activation(e_cell, e_t, e_counted, sp);     // one call site: nested calls always count (ref :505,513,526,554)
+            e_counted = true;
+            e_cell = -1;
+#pragma unroll 1
+          while (sp > 0) {
             sync();
             const uint32_t f = s.stack[sp - 1];
             const int kind = (int)(f & 3u), cell = (int)((f >> 2) & 1023u), mc = (int)(f >> 23);
@@ -795,10 +871,13 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                 if (cand < (1 << 20)) { target = cand; next = cand + 1; }
             }
             if (target < 0) { --sp; continue; }
-            const int t = typ[target];
+            e_t = typ[target];
+            e_cell = target;
             sync();                                            // deletions of this sweep are visible; frame can be updated
             if (lane == 0) s.stack[sp - 1] = frame(kind, cell, next, mc);
-            enter_activation(target, t, true, sp);             // nested calls always count (ref :505,513,526,554)
+            break;
+          }
+            if (e_cell < 0) break;
         }
         sync();
     }
@@ -1251,6 +1330,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         unsigned S = 0u, Ng = 0u;    // rows with type not in {0,1} / type < 0
         bool odd = false;
         if (in)
+#pragma unroll UNROLL_ROWS
             for (int r = 0; r < R; ++r) {
                 const int t = typ[r * C + lane], x = col[r * C + lane];
                 S |= (unsigned)not01(t) << r;
@@ -1262,9 +1342,11 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         unsigned effv = ((S & (S >> 1)) | Ng | (Ng >> 1));                       // ref :750,754
         unsigned effh = (S & from_right(S, 1)) | Ng | from_right(Ng, 1);
         unsigned unstable = 0u;
+#pragma unroll 1
         for (int k = 1; k <= K; ++k) {
             unsigned b = 0u;
             if (in)
+#pragma unroll UNROLL_ROWS
                 for (int r = 0; r < R; ++r) b |= (unsigned)(col[r * C + lane] == k) << r;
             const unsigned l1 = from_left(b, 1), l2 = from_left(b, 2), r1 = from_right(b, 1), r2 = from_right(b, 2);
             const unsigned hl = l1 & l2, hm = l1 & r1, hr = r1 & r2;      // a k-tile placed here completes a row triple
@@ -1290,6 +1372,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     __device__ void mask_to_smem(unsigned effv, unsigned effh) {
         if (lane < C) {
             const int nv = C * (R - 1);
+#pragma unroll UNROLL_ROWS
             for (int r = 0; r < R; ++r) {
                 if (r + 1 < R) s.mask[r * C + lane] = (uint8_t)((effv >> r) & 1u);
                 if (lane + 1 < C) s.mask[nv + r * (C - 1) + lane] = (uint8_t)((effh >> r) & 1u);
@@ -1457,91 +1540,160 @@ template <typename B> __device__ __forceinline__ void merge_status(B& b, const P
     if (st && b.lane == 0) p.status[b.env] |= st;
 }
 
+// ---- scheduling helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ctl_read(uint32_t* w) { return atomicAdd(w, 0u); }   // coherent read of a counter
+// Called once by every warp (k_gate) / group (k_reset) of a launch after its appends.  The last caller records the
+// range of refill requests this launch issued under its tag and, for a step, clears the other parity's work counters
+// for the next step.  Stream order makes all of it visible to the launches that follow.
+__device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers, bool is_step) {
+    __threadfence();
+    if (atomicAdd(&p.ctl[CTL_DONE], 1u) != callers - 1u) return;
+    __threadfence();
+    const uint32_t tail = ctl_read(&p.ctl[CTL_REQ_TAIL]), prev = p.ctl[CTL_REQ_PREV];
+    const int slot = p.pool_tag % PG_RING;
+    p.ctl[CTL_PG_RANGE + 2 * slot] = prev;
+    p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
+    p.ctl[CTL_PG_HEAD + slot] = 0u;
+    p.ctl[CTL_REQ_PREV] = tail;
+    if (is_step) {
+        const int nq = (p.seq & 1) ^ 1;
+        p.ctl[CTL_WL_COUNT + nq] = 0u;
+        p.ctl[CTL_WL_HEAD + nq] = 0u;
+    }
+    p.ctl[CTL_DONE] = 0u;
+}
+__device__ __forceinline__ void action_to_cells(int a, int R, int C, int& i1, int& i2) {  // ref :80-91
+    const int nv = C * (R - 1);
+    if (a < nv) { i1 = a; i2 = a + C; }
+    else {
+        const int j = a - nv;
+        const int r = j / (C - 1), c = j - r * (C - 1);
+        i1 = r * C + c; i2 = i1 + 1;
+    }
+}
+
 // TileMatchEnv.reset (ref tile_match_env.py:84-91) for the selected envs
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_reset(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.env >= p.N) return;
-    if (p.reset_mask && !p.reset_mask[gc.env]) return;
-    Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
-    b.load_cursors();
-    unsigned effv = 0u, effh = 0u;
-    if (p.init_boards) {
-        b.load_board(p.init_boards, p.init_vecw);
-        if (!b.board_is_valid()) b.status |= ST_INVALID_BOARD;
-        b.mask_bits(effv, effh);
-    } else {
-        const int ep = p.episode[gc.env] + 1;    // generate_board (ref board.py:95-112)
-        b.sync();
-        b.begin_generate((uint32_t)ep);
-        b.playability(false, true, effv, effh);
-        b.end_generate();
-        if (gc.lane == 0) { p.episode[gc.env] = ep; p.pool_req[gc.env] = p.pool_tag; }
+    if (!p.reset_mask || p.reset_mask[gc.env]) {
+        Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, gc.env);
+        b.load_cursors();
+        unsigned effv = 0u, effh = 0u;
+        if (p.init_boards) {
+            b.load_board(p.init_boards, p.init_vecw);
+            if (!b.board_is_valid()) b.status |= ST_INVALID_BOARD;
+            b.mask_bits(effv, effh);
+        } else {
+            const int ep = p.episode[gc.env] + 1;    // generate_board (ref board.py:95-112)
+            b.sync();
+            b.begin_generate((uint32_t)ep);
+            b.playability(false, true, effv, effh);
+            b.end_generate();
+            if (gc.lane == 0) {
+                p.episode[gc.env] = ep;
+                if (p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = gc.env;   // next board -> pool
+            }
+        }
+        b.store_board();
+        b.store_cursors();
+        if (!(p.flags & FLAG_NO_MASK)) { b.mask_to_smem(effv, effh); b.store_mask(); }
+        merge_status(b, p);
+        write_step_outputs<L>(p, gc.env, gc.lane, 0, 0, 0, 0, 0, 0, 0);
     }
-    b.store_board();
-    b.store_cursors();
-    if (!(p.flags & FLAG_NO_MASK)) { b.mask_to_smem(effv, effh); b.store_mask(); }
-    merge_status(b, p);
-    write_step_outputs<L>(p, gc.env, gc.lane, 0, 0, 0, 0, 0, 0, 0);
+    if (gc.lane == 0) commit_launch(p, (uint32_t)p.N, false);
 }
 
-// TileMatchEnv.step (ref tile_match_env.py:93-112)
+// TileMatchEnv.step (ref tile_match_env.py:93-112), part 1: one thread per env.  Timer / termination / error checks, the
+// effectiveness gate (ref board.py:352: the maintained mask IS is_move_effective of the current board, so a no-op
+// step reads one byte and never touches its board) and the outputs of a step that changes nothing.  Envs that need
+// board work -- an effective move, a new board, a zeroed mask -- go to the work list.
+__global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) {
+    const int env = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int wl = (int)threadIdx.x & 31;
+    const int q = p.seq & 1;
+    bool heavy = false, req = false;
+    uint32_t packed = 0u;
+    if (env < p.N) {
+        int timer = p.timer[env];
+        const int action = p.actions[env];
+        bool eff = false, regenerate = false, fault = false;
+        if (timer < 0 || timer >= p.num_moves) {
+            if (p.autoreset == AUTORESET_NEXT_STEP && timer >= p.num_moves) regenerate = true;   // this call is the reset
+            else { p.status[env] |= ST_NEEDS_RESET; fault = true; }                             // ref tile_match_env.py:94-95
+        } else if (action < 0 || action >= p.A) {                                               // ref tile_match_env.py:97
+            p.status[env] |= ST_BAD_ACTION;
+            fault = true;
+        } else if (!(p.flags & FLAG_NO_MASK)) {
+            eff = p.mask[(size_t)env * p.A + action] != 0;
+        } else {
+            const int8_t* bd = p.board + (size_t)env * 2 * p.P;
+            int i1, i2;
+            action_to_cells(action, p.R, p.C, i1, i2);
+            eff = effective_literal(bd, bd + p.P, p.R, p.C, i1, i2);
+        }
+        int terminated = 0;
+        bool zero_mask = false;
+        if (!fault) {
+            if (!regenerate) {
+                ++timer;                                                           // ref tile_match_env.py:100-101
+                terminated = timer == p.num_moves;
+                if (terminated) {
+                    if (p.autoreset == AUTORESET_SAME_STEP) { regenerate = true; timer = 0; }
+                    else zero_mask = !(p.flags & FLAG_NO_MASK);                    // ref tile_match_env.py:119-120
+                }
+            } else {
+                timer = 0;
+            }
+            p.timer[env] = timer;
+            p.moves_left[env] = p.num_moves - timer;
+        }
+        p.reward[env] = 0;
+        p.terminated[env] = (uint8_t)terminated;
+        p.is_comb[env] = 0;
+        p.new_specials[env] = 0;
+        p.activated[env] = 0;
+        p.shuffled[env] = 0;
+        // The next board is a pure function of (seed, env, episode): take it from the pool k_pregen filled ahead of
+        // time when it is there, generate it inside the step otherwise (same result either way).
+        bool from_pool = false;
+        if (regenerate) from_pool = !p.use_inj && p.pool_episode[env] == p.episode[env] + 1;
+        heavy = eff || regenerate || zero_mask;
+        req = regenerate && p.req_ring != nullptr;
+        packed = ((uint32_t)action & IT_ACTION) | (eff ? IT_EFF : 0u) | (regenerate ? IT_REGEN : 0u) |
+                 (zero_mask ? IT_ZERO_MASK : 0u) | (from_pool ? IT_FROM_POOL : 0u);
+    }
+    TMG_SITE_HERE
+    const unsigned hm = __ballot_sync(0xffffffffu, heavy), rm = __ballot_sync(0xffffffffu, req);
+    uint32_t hbase = 0u, rbase = 0u;
+    if (wl == 0) {
+        if (hm) hbase = atomicAdd(&p.ctl[CTL_WL_COUNT + q], (uint32_t)__popc(hm));
+        if (rm) rbase = atomicAdd(&p.ctl[CTL_REQ_TAIL], (uint32_t)__popc(rm));
+    }
+    hbase = (uint32_t)__shfl_sync(0xffffffffu, (int)hbase, 0);
+    rbase = (uint32_t)__shfl_sync(0xffffffffu, (int)rbase, 0);
+    const unsigned lt = (1u << wl) - 1u;
+    if (heavy) { uint2 it; it.x = (uint32_t)env; it.y = packed; p.wl_items[hbase + (uint32_t)__popc(hm & lt)] = it; }
+    if (req) p.req_ring[(rbase + (uint32_t)__popc(rm & lt)) & p.req_mask] = env;
+    __syncwarp(0xffffffffu);
+    if (wl == 0) commit_launch(p, gridDim.x * (blockDim.x >> 5), true);
+}
+
 #ifndef TMG_STEP_MIN_BLOCKS
 #define TMG_STEP_MIN_BLOCKS 6   // <= 80 registers/thread: 24 warps/SM (measured +5 % over 128 registers)
 #endif
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_step(const __grid_constant__ Params p) {
-    const GroupCtx<L> gc;
-    if (gc.env >= p.N) return;
-    const int env = gc.env, lane = gc.lane;
+// part 2 of a step, for one env of the work list: the move (ref board.py:330-395) and / or the next board
+template <int L, int RT, int CT> __device__ __forceinline__ void step_item(const Params& p, const GroupCtx<L>& gc, int env, uint32_t packed) {
+    const int lane = gc.lane;
     Board<L, RT, CT> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
     const long long prof_t0 = p.prof ? clock64() : 0;
     const bool want_mask = !(p.flags & FLAG_NO_MASK);
-    int timer = p.timer[env];
-    const int action = p.actions[env];
+    const int action = (int)(packed & IT_ACTION);
+    const bool eff = packed & IT_EFF, regenerate = packed & IT_REGEN, zero_mask = packed & IT_ZERO_MASK,
+               from_pool = packed & IT_FROM_POOL;
     unsigned effv = 0u, effh = 0u;
-    bool eff = false, have_board = false, regenerate = false;
-    if (timer < 0 || timer >= p.num_moves) {
-        if (p.autoreset == AUTORESET_NEXT_STEP && timer >= p.num_moves) {  // this call is the reset
-            regenerate = true;
-        } else {
-            b.sync();
-            if (lane == 0) p.status[env] |= ST_NEEDS_RESET;                // ref tile_match_env.py:94-95
-            write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
-            return;
-        }
-    } else if (action < 0 || action >= p.A) {                              // ref tile_match_env.py:97
-        b.sync();
-        if (lane == 0) p.status[env] |= ST_BAD_ACTION;
-        write_step_outputs<L>(p, env, lane, timer, 0, 0, 0, 0, 0, 0, false);
-        return;
-    } else if (want_mask) {
-        // effectiveness gate (ref board.py:352): the maintained mask IS is_move_effective of the current board
-        eff = p.mask[(size_t)env * p.A + action] != 0;
-    } else {
-        b.load_board(p.board, p.board_vecw);
-        have_board = true;
-        eff = b.effective_group(action);
-    }
-    b.sync();  // every lane has read timer/action/gate before any lane of the group writes state back
-    int reward = 0, is_comb = 0, shuffled = 0, terminated = 0;
-    bool zero_mask = false;
-    if (!regenerate) {
-        ++timer;                                                           // ref tile_match_env.py:100-101
-        terminated = timer == p.num_moves;
-        if (terminated) {
-            if (p.autoreset == AUTORESET_SAME_STEP) { regenerate = true; timer = 0; }
-            else zero_mask = true;                                         // ref tile_match_env.py:119-120
-        }
-    } else {
-        timer = 0;
-    }
-    // The next board is a pure function of (seed, env, episode): take it from the pool k_pregen filled ahead of
-    // time when it is there, generate it here otherwise (same result either way).
-    int next_ep = 0;
-    bool from_pool = false;
-    if (regenerate) {
-        next_ep = p.episode[env] + 1;
-        from_pool = !p.use_inj && p.pool_episode[env] == next_ep;
-    }
+    int reward = 0, is_comb = 0, shuffled = 0;
+    const int next_ep = regenerate ? p.episode[env] + 1 : 0;
     b.sync();
     const bool inline_gen = regenerate && !from_pool;
     const bool dirty = eff || inline_gen;
@@ -1552,7 +1704,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         bool clean, all_normal;
         if (phase == 0) {
             if (!eff) continue;
-            if (!have_board) b.load_board(p.board, p.board_vecw);
+            b.load_board(p.board, p.board_vecw);
             int i1, i2;
             b.action_cells(action, i1, i2);
             b.move_core(i1, i2, reward, is_comb);
@@ -1573,32 +1725,76 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         if (want_mask) copy_bytes<L>(p.mask + (size_t)env * p.A, p.pool_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
         b.status |= p.pool_status[env];
         if (eff) b.store_cursors();
+        if (p.h_board) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, 2 * p.P, p.board_vecw, lane);
+        if (want_mask && (p.h_mask || p.h_mask_bits)) {
+            copy_bytes<L>(b.s.mask, p.pool_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
+            b.sync();
+            b.mirror_mask(false);
+        }
     } else {
-        if (dirty) { b.store_board(); b.store_cursors(); }
+        if (dirty) {
+            b.store_board(); b.store_cursors();
+            if (p.h_board) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, lane);
+        }
         if (want_mask) {
-            if (zero_mask) b.store_zero_mask();
-            else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); }
+            if (zero_mask) { b.store_zero_mask(); b.mirror_mask(true); }
+            else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); b.mirror_mask(false); }
         }
     }
-    if (regenerate && lane == 0) { p.episode[env] = next_ep; p.pool_req[env] = p.pool_tag; }
     merge_status(b, p);
-    write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled);
-    if (p.prof && lane == 0) {
-        p.prof[env * 8 + 0] = (uint32_t)(clock64() - prof_t0);
-        p.prof[env * 8 + 1] = b.prof_serial;
-        p.prof[env * 8 + 2] = b.prof_rounds;
-        p.prof[env * 8 + 3] = b.prof_iters;
+    if (lane == 0) {
+        if (regenerate) p.episode[env] = next_ep;
+        if (eff) {                         // k_gate wrote the outputs of a step that changes nothing
+            p.reward[env] = reward;
+            p.is_comb[env] = (uint8_t)is_comb;
+            p.new_specials[env] = n_new;
+            p.activated[env] = n_act;
+            p.shuffled[env] = (uint8_t)shuffled;
+        }
+        if (p.prof) {
+            p.prof[env * 8 + 0] = (uint32_t)(clock64() - prof_t0);
+            p.prof[env * 8 + 1] = b.prof_serial;
+            p.prof[env * 8 + 2] = b.prof_rounds;
+            p.prof[env * 8 + 3] = b.prof_iters;
+        }
     }
 }
 
-// Fills the pool: for every env whose pool entry is not the board after its current one, generate that board
-// (and its mask).  Runs on a side stream, off the step path; touches no env state.
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
-    // Launched with a capped grid (about half of the resident-block slots) so that the step kernels always find free
-    // slots beside it; every group walks its share of the envs.
+// next index of a shared cursor for this group, or `n` and above when the list is exhausted
+template <int L> __device__ __forceinline__ uint32_t pop_item(const GroupCtx<L>& gc, uint32_t* head) {
+    uint32_t idx = 0u;
+    TMG_SITE_HERE
+    __syncwarp(gc.gmask);                  // the previous item's shared-memory traffic is complete on every lane
+    if (gc.lane == 0) idx = atomicAdd(head, 1u);
+    return (uint32_t)__shfl_sync(gc.gmask, (int)idx, gc.gshift);
+}
+
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_work(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
-    for (int env = gc.env; env < p.N; env += (int)gridDim.x * Cfg<L>::GPB) {
-        if (p.pool_req[env] != p.pool_tag) continue;   // each launch serves exactly the requests tagged for it
+    if (gc.idle) return;
+    const int q = p.seq & 1;
+    const uint32_t n = p.ctl[CTL_WL_COUNT + q];
+#pragma unroll 1
+    for (;;) {
+        const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_WL_HEAD + q]);
+        if (idx >= n) break;
+        const uint2 it = p.wl_items[idx];
+        step_item<L, RT, CT>(p, gc, (int)it.x, it.y);
+    }
+}
+
+// Fills the pool: generates the next board (and its mask) of every env whose request this launch serves.  Runs on a
+// side stream, off the step path; touches no env state.
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
+    const GroupCtx<L> gc;
+    if (gc.idle) return;
+    const int slot = p.pool_tag % PG_RING;
+    const uint32_t start = p.ctl[CTL_PG_RANGE + 2 * slot], n = p.ctl[CTL_PG_RANGE + 2 * slot + 1] - start;
+#pragma unroll 1
+    for (;;) {
+        const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_PG_HEAD + slot]);
+        if (idx >= n) break;
+        const int env = p.req_ring[(start + idx) & p.req_mask];
         const int ep = p.episode[env] + 1;
         if (p.pool_episode[env] == ep) continue;
         Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, env);

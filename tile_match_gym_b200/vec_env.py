@@ -307,8 +307,13 @@ class HostStepper:
     terminations / masks are copied back to pinned host memory, stream synchronised per call.  This is what a
     CPU-side consumer of the reference API pays, and what bench.py reports as `e2e`."""
 
-    def __init__(self, env: TileMatchVecEnv, outputs=("board", "reward", "terminated", "mask", "num_moves_left")):
+    def __init__(self, env: TileMatchVecEnv, outputs=("board", "reward", "terminated", "mask", "num_moves_left"),
+                 mirror: bool = False):
+        """mirror=True binds board / mask / mask_bits as the host mirror (tmg_host_bind): the step kernel then writes
+        the entries it changes straight into these pinned arrays over PCIe instead of copying every array in full
+        after every step; the arrays hold the complete current state after each call either way."""
         self.env = env
+        self.mirror = mirror
         N, R, Cc, A = env.num_envs, env.num_rows, env.num_cols, env.num_actions
         shapes = {"actions": ((N,), torch.int32), "board": ((N, 2, R, Cc), torch.int8), "reward": ((N,), torch.int32),
                   "terminated": ((N,), torch.uint8), "mask": ((N, A), torch.uint8),
@@ -325,6 +330,19 @@ class HostStepper:
             setattr(self.io, name, t.data_ptr())
         self.h2d_bytes = self.host["actions"].numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for n, t in self.host.items() if n != "actions")
+        if mirror:
+            ptr = lambda n: C.c_void_p(self.host[n].data_ptr()) if n in self.host else None  # noqa: E731
+            nat.check(env._lib.tmg_host_bind(env._h, ptr("board"), ptr("mask"), ptr("mask_bits"), env._stream()), "tmg_host_bind")
+            self._mirrored = [n for n in ("board", "mask", "mask_bits") if n in self.host]
+            # per step: the scalar arrays in full + one entry of every mirrored array per env that changed
+            self.d2h_bytes_fixed = sum(t.numel() * t.element_size() for n, t in self.host.items()
+                                       if n != "actions" and n not in self._mirrored)
+            self.d2h_bytes_per_changed_env = sum(self.host[n][0].numel() * self.host[n].element_size() for n in self._mirrored)
+
+    def close(self):
+        if self.mirror:
+            nat.check(self.env._lib.tmg_host_bind(self.env._h, None, None, None, self.env._stream()), "tmg_host_bind")
+            self.mirror = False
 
     def effective_actions(self, i: int):
         """The reference's info["effective_actions"] list of env i from whichever mask form was copied back."""
