@@ -220,6 +220,24 @@ def main():
     total_ms = sum(step_ms) + drain_ms
     status_bad = int((env.status != 0).sum().item())
 
+    # ---- fused rollout (tmg_step_many): the same env-steps, num_moves of them per launch ---------------------------
+    T = min(num_moves, 30)
+    n_win = max(2, args.steps // T)
+    ro_actions = [torch.randint(0, A, (T, n_local), device=dev, dtype=torch.int32, generator=gen) for _ in range(2)]
+    env.step_many(ro_actions[0]); env.join()
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record(stream)
+    for i in range(n_win):
+        if not args.no_flush:
+            flush.zero_()
+        env.step_many(ro_actions[i % 2])
+    env.join()
+    r1.record(stream)
+    barrier()
+    rollout_ms = r0.elapsed_time(r1)
+    status_bad += int((env.status != 0).sum().item())
+
     # ---- end-to-end timing through the host-buffer call (pinned host memory in and out) -----------------------
     def time_host_path(outputs, mirror=False):
         hs = HostStepper(env, outputs=outputs, mirror=mirror)
@@ -261,9 +279,9 @@ def main():
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms = t.tolist()
+        total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms = t.tolist()
         bad = torch.tensor([status_bad], device=dev); dist.all_reduce(bad); status_bad = int(bad.item())
     n_global = n_local * world
     value = n_global * args.steps / (total_ms * 1e-3)
@@ -292,6 +310,9 @@ def main():
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "tmg::k_gate + tmg::k_work<16,10,10> (one tmg_step)",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n_local,
                          "note": "integer/divergence-bound kernel: the HBM fraction is low by construction, see DESIGN.md"},
+            "rollout": {"value": n_global * T * n_win / (rollout_ms * 1e-3), "unit": UNIT, "steps_per_launch": T, "launches": n_win,
+                        "what": "tmg_step_many: the same env-steps with the actions of a whole window given up front "
+                                "(random-agent loop), boards kept on chip between steps; not the headline"},
             "clocks": clocks,
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "drain_ms": drain_ms, "wall_s": t_wall, "status_flags_set": status_bad,

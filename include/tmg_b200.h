@@ -150,6 +150,15 @@ int tmg_reset(tmg_env *env, const uint8_t *reset_mask_dev, const int8_t *init_bo
 /* actions_dev: device int32 [N].  One TileMatchEnv.step per env, cascade loop inside the kernel. */
 int tmg_step(tmg_env *env, const int32_t *actions_dev, void *stream);
 
+/* Fused rollout: num_steps successive TileMatchEnv.step calls per env in ONE launch, env e taking
+ * actions_dev[t][e] at step t (device int32 [num_steps][N]) -- the caller loop of src/examples/random_agent.py:12-31
+ * with the actions drawn up front.  State, buffers and status afterwards are exactly those of num_steps tmg_step
+ * calls (the per-step outputs in tmg_buffers are those of the last step); rewards_dev (int32) / terminated_dev
+ * (uint8), each [num_steps][N] or NULL, receive every step's reward and termination flag.  Boards stay on chip
+ * between the steps and no env waits for the longest cascade of the batch at every step. */
+int tmg_step_many(tmg_env *env, const int32_t *actions_dev, int32_t num_steps, int32_t *rewards_dev,
+                  uint8_t *terminated_dev, void *stream);
+
 /* recompute buffers.mask from the current boards (e.g. after the caller edited boards in place) */
 int tmg_legal_mask(tmg_env *env, void *stream);
 

@@ -51,6 +51,7 @@ def lib():
         L.emu_set_injected_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.emu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_void_p]
+        L.emu_step_many.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.emu_legal_mask.argtypes = [C.c_void_p]
         L.emu_debug_op.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -111,6 +112,13 @@ class EmuVecEnv:
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.int32)
         self.L.emu_step(self.h, _ptr(a))
+
+    def step_many(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        T = a.shape[0]
+        rew = np.zeros((T, self.N), np.int32); term = np.zeros((T, self.N), np.uint8)
+        self.L.emu_step_many(self.h, _ptr(a), T, _ptr(rew), _ptr(term))
+        return rew, term
 
     def legal_mask(self):
         self.L.emu_legal_mask(self.h)

@@ -45,6 +45,53 @@ def test_emulated_batch_vs_oracle(cfg):
             assert np.array_equal(getattr(e, f), getattr(o, f)), (t, f)
 
 
+@pytest.mark.parametrize("R,C,K,moves,autoreset,T", [
+    (10, 10, 4, 5, "same_step", 13), (9, 9, 6, 4, "next_step", 11), (4, 5, 3, 3, "same_step", 10), (6, 7, 4, 6, "disabled", 9),
+    (10, 10, 4, 30, "same_step", 6)])
+def test_emulated_step_many_equals_single_steps(R, C, K, moves, autoreset, T):
+    """tmg_step_many (k_rollout): T steps in one launch leave the state of T tmg_step calls and return every step's
+    reward / termination; two windows in a row so that pool hand-over between launches is covered."""
+    N = 24
+    e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=4, autoreset=autoreset, env_id_offset=11)
+    o = orc.OracleVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=4, autoreset=autoreset, env_id_offset=11, num_threads=4)
+    e.reset(); o.reset()
+    e.host_bind()
+    rng = np.random.default_rng(12)
+    fields = ["board", "timer", "draw_cursor", "shuffle_cursor", "reward", "terminated", "is_combination_match",
+              "num_new_specials", "num_specials_activated", "shuffled", "mask", "num_moves_left", "status", "episode"]
+    for window in range(2):
+        acts = rng.integers(0, o.A, (T, N)).astype(np.int32)
+        if window == 1:
+            acts[2, 5] = o.A + 3          # bad action: flagged, step does nothing (tile_match_env.py:97)
+        rew, term = e.step_many(acts)
+        for t in range(T):
+            o.step(acts[t])
+            assert np.array_equal(rew[t], o.reward) and np.array_equal(term[t], o.terminated), (window, t)
+        for f in fields:
+            assert np.array_equal(getattr(e, f), getattr(o, f)), (window, f)
+        assert np.array_equal(e.h_board, e.board) and np.array_equal(e.h_mask, e.mask)
+        e.step(acts[0]); o.step(acts[0])      # single steps and rollouts interleave
+        for f in fields:
+            assert np.array_equal(getattr(e, f), getattr(o, f)), (window, "after single step", f)
+
+
+@pytest.mark.parametrize("R,C,K", [(10, 10, 4), (9, 9, 6), (3, 5, 3), (6, 8, 3)])
+def test_emulated_thread_per_board_generator_gives_the_same_boards(R, C, K, monkeypatch):
+    """k_gen_lines (opt-in first stage of the pool refill, one thread per board on packed rows) must produce exactly
+    the boards of the group kernel: compare whole trajectories with same-step autoreset against the oracle."""
+    monkeypatch.setenv("TMG_B200_GEN_LINES", "1")
+    N, moves = 20, 3
+    e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=9, autoreset="same_step", env_id_offset=3)
+    o = orc.OracleVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=9, autoreset="same_step", env_id_offset=3, num_threads=4)
+    e.reset(); o.reset()
+    rng = np.random.default_rng(1)
+    for t in range(4 * moves):
+        a = rng.integers(0, o.A, N).astype(np.int32)
+        e.step(a); o.step(a)
+        assert np.array_equal(e.board, o.board) and np.array_equal(e.mask, o.mask), t
+        assert np.array_equal(e.shuffle_cursor, o.shuffle_cursor) and np.array_equal(e.status, o.status), t
+
+
 @pytest.mark.parametrize("R,C,K,moves,autoreset", [(10, 10, 4, 6, "same_step"), (5, 7, 3, 4, "disabled"), (9, 9, 6, 5, "next_step")])
 def test_emulated_host_mirror_tracks_device_state(R, C, K, moves, autoreset):
     """tmg_host_bind's write-through: after every step the mirror arrays equal board / mask / packed mask."""

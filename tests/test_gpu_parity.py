@@ -276,6 +276,42 @@ def test_host_mirror_write_through_matches_oracle(autoreset, R, Cc, K):
     assert env._lib.tmg_host_bind(env._h, C.c_void_p(bad.ctypes.data), None, None, env._stream()) != 0
 
 
+@pytest.mark.parametrize("R,Cc,K,moves,autoreset,T", [(10, 10, 4, 30, "same_step", 30), (10, 10, 4, 7, "same_step", 20),
+                                                      (9, 9, 6, 5, "next_step", 12), (32, 32, 7, 6, "disabled", 6),
+                                                      (6, 14, 5, 8, "same_step", 16)])
+def test_step_many_equals_single_steps(R, Cc, K, moves, autoreset, T):
+    """tmg_step_many (fused rollout): the state after T steps in one launch and every step's reward / termination
+    equal T TileMatchEnv.step calls of the oracle; rollouts and single steps interleave."""
+    torch = _torch()
+    N = 1500 if R < 32 else 96
+    inject = R == 32      # generate_board does not terminate for 32x32 / 7 colours (SURVEY 0.7): injected boards
+    g = GpuAdapter(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=21, autoreset=autoreset))
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=21, autoreset=autoreset, num_threads=8)
+    if inject:
+        z, meta = _trace_meta()
+        m32 = [m for m in meta if m["R"] == 32][0]
+        b0 = z[m32["name"] + "/init_board"].astype(np.int8)
+        boards = np.repeat(b0[None], N, axis=0)
+        g.reset(init_boards=boards); o.reset(init_boards=boards)
+    else:
+        g.env.reset(); o.reset()
+    rng = np.random.default_rng(2)
+    for window in range(3):
+        acts = rng.integers(0, o.A, (T, N)).astype(np.int32)
+        rew, term = g.env.step_many(torch.from_numpy(acts).cuda())
+        rew, term = rew.cpu().numpy(), term.cpu().numpy()
+        for t in range(T):
+            o.step(acts[t])
+            assert np.array_equal(rew[t], o.reward), (window, t)
+            assert np.array_equal(term[t].astype(np.uint8), o.terminated), (window, t)
+        assert_same(g, o, f"after rollout window {window}")
+        if autoreset == "disabled":
+            break
+        a = rng.integers(0, o.A, N).astype(np.int32)
+        g.step(a); o.step(a)
+        assert_same(g, o, f"single step after window {window}")
+
+
 def test_reset_with_seed_and_partial_reset():
     torch = _torch()
     N, R, Cc, K, moves = 600, 6, 6, 4, 50

@@ -69,6 +69,7 @@ EXPORTS = {
     "tmg_set_injected_draws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "tmg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_step_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_legal_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -92,6 +92,8 @@ struct Params {
     uint8_t* pool_mask;      // [N][A]       its legal-move mask
     int32_t* pool_episode;   // [N]          which episode the pool entry belongs to (-1 = none)
     uint32_t* pool_status;   // [N]          status bits raised while generating it (merged when it is consumed)
+    uint32_t* pool_stage;    // [N][STAGE_WORDS] line-free board of k_gen_lines awaiting k_pregen: rows, draw cursor, iterations, flags
+    int gen_bits;            // bits per cell of the thread-per-board generator (2: K <= 4, 3: K <= 8), 0 = not applicable
     int pool_tag;            // number of the k_pregen launch that serves the requests of this launch (k_gate / k_reset)
     // scheduling state (device): see Ctl below
     uint32_t* ctl;           // control words
@@ -108,6 +110,9 @@ struct Params {
     const int32_t* actions;
     const uint8_t* reset_mask;
     const int8_t* init_boards;
+    int T;                   // tmg_step_many: steps in this call; actions is [T][N]
+    int32_t* ro_reward;      // [T][N] or NULL
+    uint8_t* ro_terminated;  // [T][N] or NULL
     const int32_t* dbg_args;
     int dbg_op;
     uint32_t* prof;  // optional [N][8]: cycles total, cycles in the general path, cascade rounds, redraw iterations,
@@ -128,8 +133,11 @@ enum {
     CTL_REQ_PREV = 6,        // CTL_REQ_TAIL at the end of the previous requesting launch
     CTL_PG_RANGE = 8,        // [PG_RING][2] request range served by k_pregen launch `tag`, at tag % PG_RING
     CTL_PG_HEAD = CTL_PG_RANGE + 2 * PG_RING,   // [PG_RING] pop cursor of that launch
-    CTL_WORDS = CTL_PG_HEAD + PG_RING
+    CTL_PG_HEAD2 = CTL_PG_HEAD + PG_RING,       // [PG_RING] pop cursor of its first stage (k_gen_lines)
+    CTL_RO_HEAD = CTL_PG_HEAD2 + PG_RING,       // pop cursor of k_rollout over the envs
+    CTL_WORDS = CTL_RO_HEAD + 1
 };
+enum { STAGE_ROWS = 16, STAGE_RDC = 16, STAGE_ITERS = 17, STAGE_FLAGS = 18, STAGE_WORDS = 20 };
 enum : uint32_t { IT_ACTION = 0xfffu, IT_EFF = 1u << 12, IT_REGEN = 1u << 13, IT_ZERO_MASK = 1u << 14, IT_FROM_POOL = 1u << 15 };
 
 template <int L> struct Cfg {
@@ -200,6 +208,25 @@ template <int L> __device__ __noinline__ void copy_bytes(void* dst, const void* 
         case 2: copy_vec<L, uint16_t>(dst, src, nbytes, lane); break;
         default: copy_vec<L, uint8_t>(dst, src, nbytes, lane); break;
     }
+}
+// global -> shared copy with L2-only loads (ld.global.cg): for data another kernel may have written while this one runs
+// (an L1 line shared with a neighbouring env's entry could be stale)
+template <int L> __device__ __noinline__ void copy_bytes_cg(void* dst, const void* src, int nbytes, int vecw, int lane) {
+#ifdef TMG_EMU
+    copy_bytes<L>(dst, src, nbytes, vecw, lane);
+#else
+    if (vecw >= 4) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+#pragma unroll 1
+        for (int i = lane; i < nbytes / 4; i += L) d[i] = __ldcg(s + i);
+    } else {
+        uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(src);
+#pragma unroll 1
+        for (int i = lane; i < nbytes; i += L) d[i] = __ldcg(s + i);
+    }
+#endif
 }
 template <int L> __device__ __forceinline__ void zero_bytes(void* dst, int nbytes, int vecw, int lane) {
     if (vecw >= 4) {
@@ -1385,9 +1412,9 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     // ===================================================================================================
     // `clean`: the caller knows the board has no lines.  `all_normal`: every tile has type 1 (fresh board).
     // Leaves the mask bits of the final board in effv/effh.
-    __device__ __forceinline__ bool playability(bool clean, bool all_normal, unsigned& effv, unsigned& effh) {
+    __device__ __forceinline__ bool playability(bool clean, bool all_normal, unsigned& effv, unsigned& effh, int iters0 = 0) {
         bool shuffled = false;
-        int iters = 0, from = R - 1;
+        int iters = iters0, from = R - 1;
 #pragma unroll 1
         for (;;) {
             bool capped = false;
@@ -1554,7 +1581,9 @@ __device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers,
     p.ctl[CTL_PG_RANGE + 2 * slot] = prev;
     p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
     p.ctl[CTL_PG_HEAD + slot] = 0u;
+    p.ctl[CTL_PG_HEAD2 + slot] = 0u;
     p.ctl[CTL_REQ_PREV] = tail;
+    p.ctl[CTL_RO_HEAD] = 0u;
     if (is_step) {
         const int nq = (p.seq & 1) ^ 1;
         p.ctl[CTL_WL_COUNT + nq] = 0u;
@@ -1680,7 +1709,7 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
 }
 
 #ifndef TMG_STEP_MIN_BLOCKS
-#define TMG_STEP_MIN_BLOCKS 6   // <= 80 registers/thread: 24 warps/SM (measured +5 % over 128 registers)
+#define TMG_STEP_MIN_BLOCKS 8   // <= 64 registers/thread: 32 warps/SM.  Measured (65 536 envs): 4 blocks 183 M, 6 198 M, 8 228 M, 10 203 M steps/s
 #endif
 // part 2 of a step, for one env of the work list: the move (ref board.py:330-395) and / or the next board
 template <int L, int RT, int CT> __device__ __forceinline__ void step_item(const Params& p, const GroupCtx<L>& gc, int env, uint32_t packed) {
@@ -1783,8 +1812,221 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
     }
 }
 
-// Fills the pool: generates the next board (and its mask) of every env whose request this launch serves.  Runs on a
-// side stream, off the step path; touches no env state.
+// Fused multi-step rollout (the caller loop of src/examples/random_agent.py:12-31 with given actions):
+// T successive TileMatchEnv.step calls per env in ONE launch.  A group keeps its env's board in shared memory and its
+// legal-move mask as bitboards in registers across the steps, so a step that changes nothing is a bit test, and no
+// env ever waits for the slowest cascade of the batch.  State and outputs after the call are those of T tmg_step
+// calls; per-step rewards / terminations go to [T][N] arrays.
+template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_rollout(const __grid_constant__ Params p) {
+    const GroupCtx<L> gc;
+    if (gc.idle) return;
+    const int lane = gc.lane;
+    const bool want_mask = !(p.flags & FLAG_NO_MASK);
+#pragma unroll 1
+    for (;;) {
+        const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_RO_HEAD]);
+        if (idx >= (uint32_t)p.N) break;
+        const int env = (int)idx;
+        Board<L, RT, CT> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
+        b.load_cursors();
+        int timer = p.timer[env], episode = p.episode[env];
+        b.load_board(p.board, p.board_vecw);
+        unsigned effv = 0u, effh = 0u;
+        bool have_mask = false, regenerated = false, pool_used = false, touched = false;
+        int reward = 0, is_comb = 0, shuffled = 0, terminated = 0, n_new = 0, n_act = 0;
+#pragma unroll 1
+        for (int t = 0; t < p.T; ++t) {
+            const int action = p.actions[(size_t)t * p.N + env];
+            reward = 0; is_comb = 0; shuffled = 0; terminated = 0; n_new = 0; n_act = 0;
+            bool eff = false, regenerate = false, fault = false;
+            if (timer < 0 || timer >= p.num_moves) {
+                if (p.autoreset == AUTORESET_NEXT_STEP && timer >= p.num_moves) regenerate = true;   // this step is the reset
+                else { b.status |= ST_NEEDS_RESET; fault = true; }                                  // ref tile_match_env.py:94-95
+            } else if (action < 0 || action >= p.A) {                                               // ref tile_match_env.py:97
+                b.status |= ST_BAD_ACTION;
+                fault = true;
+            } else {
+                if (!have_mask) { b.mask_bits(effv, effh); have_mask = true; }
+                // effectiveness gate (ref board.py:352): bit (r, c) of the mask bitboards, held by lane c
+                const int nv = b.C * (b.R - 1);
+                const bool vert = action < nv;
+                const int j = vert ? action : action - nv, w = vert ? b.C : b.C - 1;
+                const int r = j / w, c = j - r * w;
+                eff = ((unsigned)b.shfl((int)(vert ? effv : effh), c) >> r) & 1u;
+            }
+            if (!fault) {
+                if (!regenerate) {
+                    ++timer;                                                       // ref tile_match_env.py:100-101
+                    terminated = timer == p.num_moves;
+                    if (terminated && p.autoreset == AUTORESET_SAME_STEP) { regenerate = true; timer = 0; }
+                } else {
+                    timer = 0;
+                }
+                if (eff) {
+                    int i1, i2;
+                    b.action_cells(action, i1, i2);
+                    b.move_core(i1, i2, reward, is_comb);
+                    shuffled = b.playability(true, false, effv, effh);             // ref board.py:381-391
+                    n_new = b.n_new; n_act = b.n_act;
+                    touched = true;
+                }
+                if (regenerate) {
+                    ++episode;
+                    // The pool entry may be completed by a k_pregen launch that runs beside this kernel: its episode number is
+                    // published last (after a fence), so read it first, fence, then read the entry past the L1.
+                    bool in_pool = false;
+                    if (!p.use_inj && !pool_used) {
+                        int pe = 0;
+                        if (lane == 0) pe = (int)ctl_read(reinterpret_cast<uint32_t*>(p.pool_episode + env));
+                        in_pool = b.shfl(pe, 0) == episode;
+                    }
+                    if (in_pool) {                                                  // the pool holds this board
+                        __threadfence();
+                        b.sync();
+                        copy_bytes_cg<L>(b.s.board, p.pool_board + (size_t)env * 2 * p.P, 2 * p.P, p.board_vecw, lane);
+                        if (lane == 0) b.status |= ctl_read(p.pool_status + env);
+                        b.sync();
+                        b.mask_bits(effv, effh);
+                        pool_used = true;
+                    } else {
+                        b.begin_generate((uint32_t)episode);                       // ref board.py:95-112
+                        b.playability(false, true, effv, effh);
+                        b.end_generate();
+                    }
+                    have_mask = true; regenerated = true; touched = true;
+                }
+            }
+            if (lane == 0) {
+                if (p.ro_reward) p.ro_reward[(size_t)t * p.N + env] = reward;
+                if (p.ro_terminated) p.ro_terminated[(size_t)t * p.N + env] = (uint8_t)terminated;
+            }
+        }
+        // state and last-step outputs, as T tmg_step calls would leave them
+        const bool terminal = timer == p.num_moves;                               // all-zero mask (ref tile_match_env.py:119-120)
+        if (touched) { b.store_board(); b.store_cursors(); }
+        if (want_mask && p.T > 0) {
+            if (terminal) b.store_zero_mask();
+            else if (touched) { b.mask_to_smem(effv, effh); b.store_mask(); }
+        }
+        if (p.h_board && touched) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, lane);
+        if (want_mask && p.T > 0 && (terminal || touched)) b.mirror_mask(terminal);
+        merge_status(b, p);
+        if (lane == 0) {
+            p.episode[env] = episode;
+            if (regenerated && p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = env;   // next board -> pool
+        }
+        write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled, timer >= 0);
+        b.sync();
+    }
+    if (lane == 0) commit_launch(p, gridDim.x * (uint32_t)Cfg<L>::GPB, false);
+}
+
+// =====================================================================================================
+// generate_board (ref board.py:95-112), first stage: ONE THREAD per board.
+// A fresh board is all normal tiles, so it is colours only: a row is one 32-bit word of BITS-bit cells (value =
+// colour - 1), the R rows of a thread sit in its private column of shared memory.  remove_colour_lines (ref :120-131)
+// then needs no cross-lane traffic at all: the line scan is a handful of xor / shift / and per row, from the bottom
+// row up to the first row with a line, and the redraw turns Philox blocks straight into row words.  About 86 such
+// iterations per 10x10 / 4-colour board (max > 500), each a dependent chain: one board per thread keeps 32 of them in
+// flight per warp instead of 2, and a thread that finishes its board takes the next request.  Produces the line-free
+// board; possible_move / shuffle (ref :102-109), rare, and the mask are left to k_pregen (second stage).
+// Draws: the episode-indexed reset stream, cell i of a redraw takes word rdc + i -- exactly as Board::draw_cells.
+// =====================================================================================================
+template <int BITS> __device__ __forceinline__ uint32_t gen_eq(uint32_t t) {   // cells of t that are all-zero -> their low bit
+    if (BITS == 2) return ~(t | (t >> 1)) & 0x55555555u;
+    return ~(t | (t >> 1) | (t >> 2)) & 0x09249249u;
+}
+template <int BITS> __global__ void __launch_bounds__(128) k_gen_lines(const __grid_constant__ Params p) {
+    extern __shared__ __align__(16) unsigned char tmg_smem_raw[];
+    uint32_t* rows = reinterpret_cast<uint32_t*>(tmg_smem_raw) + threadIdx.x;   // row r of this thread: rows[r * 128]
+    const int R = p.R, C = p.C;
+    const uint32_t K = (uint32_t)p.K;
+    const int slot = p.pool_tag % PG_RING;
+    const uint32_t start = p.ctl[CTL_PG_RANGE + 2 * slot], n_req = p.ctl[CTL_PG_RANGE + 2 * slot + 1] - start;
+    const uint32_t cells = (BITS == 2) ? 0x55555555u : 0x09249249u;
+    const uint32_t cmask = (C * BITS >= 32) ? cells : (cells & ((1u << (C * BITS)) - 1u));   // low bit of cells 0..C-1
+    const uint32_t hmask = cmask & ((1u << ((C - 1) * BITS)) - 1u);                         // cells 0..C-2
+    int env = -1, iters = 0, from = 0, n_draw = 0;
+    uint32_t ep = 0u, gid = 0u, rdc = 0u;
+#pragma unroll 1
+    for (;;) {
+        if (env < 0) {                                          // take the next request
+            const uint32_t idx = atomicAdd(&p.ctl[CTL_PG_HEAD2 + slot], 1u);
+            if (idx >= n_req) break;
+            env = p.req_ring[(start + idx) & p.req_mask];
+            ep = (uint32_t)(p.episode[env] + 1);
+            if (p.pool_episode[env] == (int)ep) { env = -1; continue; }
+            gid = (uint32_t)(p.env_id_offset + (uint64_t)env);
+            rdc = 0u; iters = 0;
+            n_draw = R * C;                                      // ref :96-97: the initial fill
+            from = R - 1;
+        }
+        {   // cells [0, n_draw) in row-major order <- the next n_draw draws (ref :97 / :129); n_draw is whole rows
+            uint32_t blk = rdc >> 2;
+            int skip = (int)(rdc & 3u), i = 0, r = 0, c = 0;
+            uint32_t acc = 0u;
+#pragma unroll 1
+            while (i < n_draw) {
+                uint32_t w[4];
+                philox4x32_10(blk, ep, gid, 3u, p.key0, p.key1, w);
+                ++blk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < skip || i >= n_draw) continue;
+                    acc |= __umulhi(w[j], K) << (c * BITS);
+                    ++i;
+                    if (++c == C) { rows[r * 128] = acc; ++r; c = 0; acc = 0u; }
+                }
+                skip = 0;
+            }
+            rdc += (uint32_t)n_draw;
+        }
+        // line scan from row `from` upwards to the bottom-most row with an anchored line (ref :149-196, all tiles normal)
+        int rs = from;
+        uint32_t x0 = rows[rs * 128], x1 = rs >= 1 ? rows[(rs - 1) * 128] : 0u, x2 = rs >= 2 ? rows[(rs - 2) * 128] : 0u;
+        uint32_t H = 0u, V = 0u;
+#pragma unroll 1
+        for (;;) {
+            const uint32_t e = gen_eq<BITS>(x0 ^ (x0 >> BITS)) & hmask;   // cell == right neighbour
+            H = e & (e >> BITS);                                          // left end of a horizontal triple (ref :179-189)
+            V = rs >= 2 ? (gen_eq<BITS>(x0 ^ x1) & gen_eq<BITS>(x1 ^ x2) & cmask) : 0u;   // bottom of a vertical triple (ref :163-173)
+            if ((H | V) || rs == 0) break;
+            --rs;
+            x0 = x1; x1 = x2; x2 = rs >= 2 ? rows[(rs - 2) * 128] : 0u;
+        }
+        bool capped = false;
+        if (H | V) {
+            if (iters < p.max_iters) {                         // remove_colour_lines (ref :120-131)
+                ++iters;
+                const int cv = V ? (__ffs((int)V) - 1) : 1024, ch = H ? (__ffs((int)H) - 1) : 1024;   // bit positions: same order as columns
+                int top = rs;                                  // first line horizontal: l[0][0] is in row rs
+                if (cv <= ch) {                                // vertical lines are listed first at the same column (ref :163,179)
+                    top = rs - 2;
+                    const uint32_t sel = ((1u << BITS) - 1u) << cv;
+#pragma unroll 1
+                    while (top >= 1 && ((rows[(top - 1) * 128] ^ x2) & sel) == 0u) --top;   // x2 = row rs-2: extend upwards (ref :168-172)
+                }
+                const int row = min(R - 1, top + 1);
+                n_draw = (row + 1) * C;
+                from = min(R - 1, max(rs, row + 2));           // rows below were line-free and none of their 3-windows changed
+                continue;
+            }
+            capped = true;
+        }
+        // line-free (or capped): hand the board to the second stage
+        uint32_t* st = p.pool_stage + (size_t)env * STAGE_WORDS;
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) st[r] = rows[r * 128];
+        st[STAGE_RDC] = rdc;
+        st[STAGE_ITERS] = (uint32_t)iters;
+        st[STAGE_FLAGS] = capped ? 1u : 0u;
+        env = -1;
+    }
+}
+
+// Second stage of the pool refill (or all of it when k_gen_lines does not apply): possible_move / shuffle and the mask
+// of the next board of every env whose request this launch serves.  Runs on a side stream, off the step path; touches
+// no env state.
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
@@ -1800,8 +2042,28 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, env);
         unsigned effv = 0u, effh = 0u;
         b.sync();
-        b.begin_generate((uint32_t)ep);
-        b.playability(false, true, effv, effh);
+        if (p.gen_bits) {                      // the line-free board comes from k_gen_lines: expand it to bytes
+            const uint32_t* st = p.pool_stage + (size_t)env * STAGE_WORDS;
+            const int BITS = p.gen_bits;
+            b.episode = (uint32_t)ep;
+            b.in_reset = true;
+            b.rdc = (uint64_t)st[STAGE_RDC]; b.rsc = 0ull;
+            const int iters0 = (int)st[STAGE_ITERS];
+            const bool capped = st[STAGE_FLAGS] & 1u;
+            if (gc.lane < b.C) {
+#pragma unroll 1
+                for (int r = 0; r < b.R; ++r) {
+                    b.col[r * b.C + gc.lane] = (int8_t)(1 + (int)((st[r] >> (gc.lane * BITS)) & ((1u << BITS) - 1u)));
+                    b.typ[r * b.C + gc.lane] = 1;
+                }
+            }
+            b.sync();
+            if (capped) { b.status |= ST_RESET_CAP; b.mask_bits(effv, effh); }
+            else b.playability(true, true, effv, effh, iters0);
+        } else {
+            b.begin_generate((uint32_t)ep);
+            b.playability(false, true, effv, effh);
+        }
         b.end_generate();
         b.sync();
         copy_bytes<L>(p.pool_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, gc.lane);

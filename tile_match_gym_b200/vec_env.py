@@ -243,6 +243,23 @@ class TileMatchVecEnv:
         }
         return self._obs(), self.reward, self.terminated, self.truncated, info
 
+    def step_many(self, actions):
+        """T successive steps in one launch (tmg_step_many).  actions: (T, N) integer tensor, env e takes
+        actions[t, e] at step t.  Returns (rewards (T, N) int32, terminations (T, N) bool); the env's buffers and
+        observations afterwards are those after the last step."""
+        a = torch.as_tensor(actions)
+        if a.device != self.device or a.dtype != torch.int32 or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=torch.int32).contiguous()
+        if a.dim() != 2 or a.shape[1] != self.num_envs:
+            raise ValueError("actions must have shape (T, num_envs)")
+        T = a.shape[0]
+        rew = torch.empty((T, self.num_envs), dtype=torch.int32, device=self.device)
+        term = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self.device)
+        nat.check(self._lib.tmg_step_many(self._h, C.c_void_p(a.data_ptr()), T, C.c_void_p(rew.data_ptr()),
+                                          C.c_void_p(term.data_ptr()), self._stream()), "tmg_step_many")
+        self._last_actions = a
+        return rew, term.view(torch.bool)
+
     def join(self) -> None:
         """Make the current stream wait for the board generations queued on the library's side stream."""
         nat.check(self._lib.tmg_join(self._h, self._stream()), "tmg_join")
