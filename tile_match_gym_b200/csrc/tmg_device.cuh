@@ -331,12 +331,12 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     const int lane;
     const unsigned gmask;
     const int gshift;
-    const int env;
+    int env;
     const int R, C, P, K;
     int8_t* const col;
     int8_t* const typ;
     uint64_t dcur, scur;
-    const uint32_t gid;
+    uint32_t gid;
     uint32_t status;
     int n_new, n_act;  // counters, uniform after broadcast (ref :343-344)
     uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
@@ -352,6 +352,13 @@ template <int L, int RT = 0, int CT = 0> struct Board {
           P(RT ? RT * CT : pp.P), K(pp.K), col(sm.board), typ(sm.board + (RT ? RT * CT : pp.P)), dcur(0), scur(0),
           gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)), status(0), n_new(0), n_act(0), specials(pp.specials),
           prof_on(pp.prof != nullptr) {}
+
+    // the same group moves on to another env (persistent loops that keep one Board object across their iterations)
+    __device__ __forceinline__ void rebind(int env_) {
+        env = env_;
+        gid = (uint32_t)(p.env_id_offset + (uint64_t)env_);
+        status = 0u; n_new = 0; n_act = 0; dcur = 0ull; scur = 0ull;
+    }
 
     // ---- group collectives ---------------------------------------------------------------------------
     __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
@@ -1448,6 +1455,23 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         }
     }
 
+    // One iteration of remove_colour_lines on a fresh (all-normal) board (ref :120-131), the unit of work of k_pregen's
+    // warp-converged loop.  Returns true if a line was found and the rows above it were redrawn, false when the board
+    // is line-free (or the iteration cap was hit: `capped`).  Same arithmetic as the loop in playability().
+    __device__ __forceinline__ bool redraw_iteration(int& from, int& iters, bool& capped) {
+        sync();
+        const Scan sc = scan_lines(from, true);
+        if (sc.rstar < 0) return false;
+        if (iters >= p.max_iters) { status |= ST_RESET_CAP; capped = true; return false; }
+        ++iters;
+        ++prof_iters;
+        const int top = first_line_top(sc);
+        const int row = min(R - 1, top + 1);
+        draw_cells((row + 1) * C, false);
+        from = min(R - 1, max(sc.rstar, row + 2));
+        return true;
+    }
+
     // move (ref :330-378) after the effectiveness gate, up to but excluding the playability loop
     __device__ void move_core(int i1, int i2, int& elim_out, int& is_comb) {
         n_new = 0; n_act = 0;                                // ref :343-347
@@ -2024,48 +2048,75 @@ template <int BITS> __global__ void __launch_bounds__(128) k_gen_lines(const __g
     }
 }
 
-// Second stage of the pool refill (or all of it when k_gen_lines does not apply): possible_move / shuffle and the mask
-// of the next board of every env whose request this launch serves.  Runs on a side stream, off the step path; touches
-// no env state.
+// Pool refill: generate_board (ref board.py:95-112) of the next board of every env whose request this launch serves
+// (with k_gen_lines enabled, only its second stage: possible_move / shuffle and the mask).  Runs on a side stream,
+// off the step path; touches no env state.
+// The kernel is issue-bound (ncu: 70 % issue slots busy, instruction-cache hit rate 99.98 %), and a board needs ~86
+// identical scan + redraw iterations, so the groups of a warp are kept CONVERGED: the loop below is one iteration per
+// trip for every group of the warp, with a warp-wide reconvergence point at the top, and a group that finishes its
+// board takes the next request inside the same loop.  One warp instruction then serves all the boards of the warp.
+template <int L> __device__ __forceinline__ bool warp_all_done(bool done) {
+#ifdef TMG_EMU
+    return done;               // the emulator runs one group at a time
+#else
+    constexpr unsigned wmask = (Cfg<L>::GPW * L >= 32) ? 0xffffffffu : ((1u << ((Cfg<L>::GPW * L) & 31)) - 1u);
+    return __all_sync(wmask, done);
+#endif
+}
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
     const int slot = p.pool_tag % PG_RING;
     const uint32_t start = p.ctl[CTL_PG_RANGE + 2 * slot], n = p.ctl[CTL_PG_RANGE + 2 * slot + 1] - start;
+    Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, 0);
+    bool have = false, done = false, capped = false, staged = false;
+    int from = 0, iters = 0, ep = 0;
 #pragma unroll 1
     for (;;) {
-        const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_PG_HEAD + slot]);
-        if (idx >= n) break;
-        const int env = p.req_ring[(start + idx) & p.req_mask];
-        const int ep = p.episode[env] + 1;
-        if (p.pool_episode[env] == ep) continue;
-        Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, env);
-        unsigned effv = 0u, effh = 0u;
-        b.sync();
-        if (p.gen_bits) {                      // the line-free board comes from k_gen_lines: expand it to bytes
-            const uint32_t* st = p.pool_stage + (size_t)env * STAGE_WORDS;
-            const int BITS = p.gen_bits;
-            b.episode = (uint32_t)ep;
-            b.in_reset = true;
-            b.rdc = (uint64_t)st[STAGE_RDC]; b.rsc = 0ull;
-            const int iters0 = (int)st[STAGE_ITERS];
-            const bool capped = st[STAGE_FLAGS] & 1u;
-            if (gc.lane < b.C) {
+        if (warp_all_done<L>(done)) break;     // also the reconvergence point of the warp's groups
+        if (!done && !have) {                  // take the next request
+            const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_PG_HEAD + slot]);
+            if (idx >= n) done = true;
+            else {
+                const int env = p.req_ring[(start + idx) & p.req_mask];
+                ep = p.episode[env] + 1;
+                if (p.pool_episode[env] != ep) {
+                    b.rebind(env);
+                    b.sync();
+                    capped = false; from = b.R - 1; iters = 0; have = true;
+                    staged = p.gen_bits != 0;
+                    if (staged) {              // the line-free board comes from k_gen_lines: expand it to bytes
+                        const uint32_t* st = p.pool_stage + (size_t)env * STAGE_WORDS;
+                        const int BITS = p.gen_bits;
+                        b.episode = (uint32_t)ep;
+                        b.in_reset = true;
+                        b.rdc = (uint64_t)st[STAGE_RDC]; b.rsc = 0ull;
+                        iters = (int)st[STAGE_ITERS];
+                        capped = st[STAGE_FLAGS] & 1u;
+                        if (capped) b.status |= ST_RESET_CAP;
+                        if (gc.lane < b.C) {
 #pragma unroll 1
-                for (int r = 0; r < b.R; ++r) {
-                    b.col[r * b.C + gc.lane] = (int8_t)(1 + (int)((st[r] >> (gc.lane * BITS)) & ((1u << BITS) - 1u)));
-                    b.typ[r * b.C + gc.lane] = 1;
+                            for (int r = 0; r < b.R; ++r) {
+                                b.col[r * b.C + gc.lane] = (int8_t)(1 + (int)((st[r] >> (gc.lane * BITS)) & ((1u << BITS) - 1u)));
+                                b.typ[r * b.C + gc.lane] = 1;
+                            }
+                        }
+                        b.sync();
+                    } else {
+                        b.begin_generate((uint32_t)ep);        // ref :96-97
+                    }
                 }
             }
-            b.sync();
-            if (capped) { b.status |= ST_RESET_CAP; b.mask_bits(effv, effh); }
-            else b.playability(true, true, effv, effh, iters0);
-        } else {
-            b.begin_generate((uint32_t)ep);
-            b.playability(false, true, effv, effh);
         }
+        if (!have) continue;
+        if (!staged && b.redraw_iteration(from, iters, capped)) continue;   // ref :99-101, one iteration
+        // line-free: possible_move / shuffle (ref :102-109, rare) and the mask, then publish the pool entry
+        unsigned effv = 0u, effh = 0u;
+        if (capped) b.mask_bits(effv, effh);
+        else b.playability(true, true, effv, effh, iters);
         b.end_generate();
         b.sync();
+        const int env = b.env;
         copy_bytes<L>(p.pool_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, gc.lane);
         if (!(p.flags & FLAG_NO_MASK)) {
             b.mask_to_smem(effv, effh);
@@ -2078,6 +2129,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         b.sync();
         if (gc.lane == 0) p.pool_episode[env] = ep;
         b.sync();
+        have = false;
     }
 }
 
