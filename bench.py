@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A "step" is one TileMatchEnv.step over the whole batch of synthetic envs: swap, effectiveness gate,
+A "step" is one TileMatchEnv.step (one tmg_step call = k_gate + k_work) over the whole batch of synthetic envs: swap, effectiveness gate,
 combination match, full cascade loop (detect / classify / activate / gravity / refill until stable),
 playability repair, timer/termination, legal-move mask, and the autoreset (generate_board) of every env whose
 episode ended.  Workload = BASELINE.json configs[1]: 10x10, 4 colours, cookie + v/h laser + bomb,
@@ -15,7 +15,9 @@ spreads the episode phases instead (1/30 of the envs reset in every step).
 
 Prints ONE JSON line (rank 0).  `value` times tmg_step with inputs resident in HBM (CUDA events around each
 launch, L2 flushed between steps); `e2e` times the host-buffer call tmg_step_host (actions from pinned host
-memory, board/reward/terminated/mask/num_moves_left copied back every step).
+memory; board, reward, terminated, bit-packed mask and num_moves_left complete in pinned host memory after every step,
+the board and mask through the host mirror the kernel writes directly, stream synchronised per step); `rollout`
+reports tmg_step_many beside them.
 """
 import argparse
 import json
@@ -37,9 +39,9 @@ P = ROWS * COLS
 A = 2 * P - ROWS - COLS
 # algorithmic bytes per env-step = 4P + 48 + A = 628 B for 10x10 (int8 planes in+out, scalars, mask)
 BYTES_PER_STEP = 4 * P + 48 + A
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch (ncu --set full, profiles/r01_k_step_ncu_raw.txt):
-# 13.6 MB read + ~0 written (no-op steps never load the board; writes stay in the 126 MB L2 within a launch)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 13.65e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch (ncu --set full, profiles/r01b_k_work_ncu.txt):
+# 5.78 MB read + 0.20 MB written (no-op steps never load their board; writes stay in the 126 MB L2 within a launch)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 5.98e6
 METRIC = "env-steps/sec (full cascade, bit-exact)"
 UNIT = "env-steps/s"
 
@@ -57,7 +59,7 @@ class ClockSampler(threading.Thread):
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0, period=0.2):
+    def __init__(self, index=0, period=0.05):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.stop_flag = index, period, [], threading.Event()
 
