@@ -202,10 +202,10 @@ void* emu_create(const emu_config* c) {
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
     size_t cap = 1;
     while (cap < N) cap <<= 1;
-    size_t o[22] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
+    size_t o[23] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
                     take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4), take(N * 4), take(N * 4),
                     take(N * 2 * p.P), take(N * p.A), take(N * 4), take(CTL_WORDS * 4), take(N * 8), take(cap * 4),
-                    take(N * STAGE_WORDS * 4)};
+                    take(N * STAGE_WORDS * 4), take(N)};
     e->mem.assign(off + 256, 0);
     char* b = e->mem.data();
     b += (256 - ((uintptr_t)b & 255)) & 255;
@@ -219,7 +219,7 @@ void* emu_create(const emu_config* c) {
     p.ctl = (uint32_t*)(b + o[18]); p.wl_items = (uint2*)(b + o[19]); p.req_mask = (uint32_t)(cap - 1);
     const bool pregen = !p.use_inj && !(p.flags & 2u) && p.autoreset != 0;
     p.req_ring = pregen ? (int32_t*)(b + o[20]) : nullptr;
-    p.pool_stage = (uint32_t*)(b + o[21]);
+    p.pool_stage = (uint32_t*)(b + o[21]); p.n_special = (uint8_t*)(b + o[22]);
     if (pregen && p.R <= STAGE_ROWS && getenv("TMG_B200_GEN_LINES")) {
         if (p.K <= 4 && 2 * p.C <= 32) p.gen_bits = 2;
         else if (p.K <= 8 && 3 * p.C <= 32) p.gen_bits = 3;

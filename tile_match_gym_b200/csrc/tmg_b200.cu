@@ -235,7 +235,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
                  o_pool_status = take((size_t)N * 4), o_mask_bits = take((size_t)N * ((p.A + 7) / 8)),
                  o_ctl = take((size_t)CTL_WORDS * 4), o_items = take((size_t)N * sizeof(uint2)),
-                 o_stage = take((size_t)N * STAGE_WORDS * 4);
+                 o_stage = take((size_t)N * STAGE_WORDS * 4), o_nsp = take((size_t)N);
     size_t req_cap = 1;
     while (req_cap < (size_t)N) req_cap <<= 1;
     const size_t o_ring = take(req_cap * 4);
@@ -266,6 +266,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.wl_items = reinterpret_cast<uint2*>(b + o_items);
     p.req_mask = (uint32_t)(req_cap - 1);
     p.pool_stage = reinterpret_cast<uint32_t*>(b + o_stage);
+    p.n_special = reinterpret_cast<uint8_t*>(b + o_nsp);
     e->mask_bits_dev = reinterpret_cast<uint8_t*>(b + o_mask_bits);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;

@@ -97,7 +97,8 @@ struct Params {
     int pool_tag;            // number of the k_pregen launch that serves the requests of this launch (k_gate / k_reset)
     // scheduling state (device): see Ctl below
     uint32_t* ctl;           // control words
-    uint2* wl_items;         // [N] work list of the current step: {env, action | flags << 12}
+    uint2* wl_items;         // [N] work list of the current step: {env, action | flags << 12}; high priority from the front, rest from the back
+    uint8_t* n_special;      // [N] special tiles on the env's board (scheduling hint only: a stale value costs time, never correctness)
     int32_t* req_ring;       // [req_mask + 1] envs whose pool entry must be refilled, in request order (NULL: pool not in use)
     uint32_t req_mask;       // ring capacity - 1 (capacity = power of two >= N)
     int seq;                 // number of this tmg_step call: its parity selects the work-list counters
@@ -135,8 +136,11 @@ enum {
     CTL_PG_HEAD = CTL_PG_RANGE + 2 * PG_RING,   // [PG_RING] pop cursor of that launch
     CTL_PG_HEAD2 = CTL_PG_HEAD + PG_RING,       // [PG_RING] pop cursor of its first stage (k_gen_lines)
     CTL_RO_HEAD = CTL_PG_HEAD2 + PG_RING,       // pop cursor of k_rollout over the envs
-    CTL_WORDS = CTL_RO_HEAD + 1
+    CTL_WL_COUNT_LO = CTL_RO_HEAD + 1,          // [2] normal-priority items (CTL_WL_COUNT counts the high-priority ones)
+    CTL_WORDS = CTL_WL_COUNT_LO + 2
 };
+enum { PRI_SPECIALS = 4 };   // a move on a board with this many special tiles is scheduled first: 23 % of the effective
+                             // moves, 80 % of the longest 1 % of the cascades (10x10, 4 colours, measured on the CPU restatement)
 enum { STAGE_ROWS = 16, STAGE_RDC = 16, STAGE_ITERS = 17, STAGE_FLAGS = 18, STAGE_WORDS = 20 };
 enum : uint32_t { IT_ACTION = 0xfffu, IT_EFF = 1u << 12, IT_REGEN = 1u << 13, IT_ZERO_MASK = 1u << 14, IT_FROM_POOL = 1u << 15 };
 
@@ -339,6 +343,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     uint32_t gid;
     uint32_t status;
     int n_new, n_act;  // counters, uniform after broadcast (ref :343-344)
+    unsigned last_S = 0u;  // special tiles of this lane's column as of the last mask_bits (scheduling hint, see n_special)
     uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
     const uint32_t specials;   // copies of the Params fields the round code needs (no pointer chasing out of line)
     const bool prof_on;
@@ -1371,6 +1376,7 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                 Ng |= (unsigned)(t < 0) << r;
                 odd |= (t < 0) != (x == 0);
             }
+        last_S = S;
         const unsigned rows = rows_mask();
         const unsigned rows_v = rows >> 1;  // rows r with r+1 < R
         unsigned effv = ((S & (S >> 1)) | Ng | (Ng >> 1));                       // ref :750,754
@@ -1472,10 +1478,12 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         return true;
     }
 
-    // move (ref :330-378) after the effectiveness gate, up to but excluding the playability loop
-    __device__ void move_core(int i1, int i2, int& elim_out, int& is_comb) {
+    // move (ref :330-378) after the effectiveness gate, in the pieces the kernels schedule:
+    // move_begin = counters, swap and the combination match (ref :343-361), returns is_combination_match -- its
+    // gravity + refill (ref :362-364) is left to the first cascade_trip; cascade_trip = one trip of the cascade
+    // loop (ref :367-376), returns false when the board is stable.  One call site of fall_and_refill / resolve_round.
+    __device__ __forceinline__ bool move_begin(int i1, int i2) {
         n_new = 0; n_act = 0;                                // ref :343-347
-        int elim = 0;
         sync();
         if (lane == 0) {                                     // swap_coords (ref :355, :729-732)
             const int8_t a = col[i1], b = typ[i1];
@@ -1485,22 +1493,29 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         sync();
         const int t1 = typ[i1], t2 = typ[i2];
         const bool comb = (not01(t1) && not01(t2)) || t1 < 0 || t2 < 0;  // ref :357-359
-        is_comb = comb;
         sync();  // every lane has read the swapped types before the leader starts deleting
         if (comb) {
             const SlowOut o = slow_combination<L, RT, CT>(&s, &p, lane, gmask, gshift, env, i1, i2);  // ref :361
             n_new = o.n_new; n_act = o.n_act; status |= o.status;
-            int e_cnt;
-            fall_and_refill(e_cnt);                          // ref :362-364
-            elim += e_cnt;
         }
+        return comb;
+    }
+    __device__ __forceinline__ bool cascade_trip(bool& pending_fall, int& elim) {
+        int lines = 0;
+        if (!pending_fall) lines = resolve_round();          // ref :369-373
+        if (!pending_fall && lines == 0) return false;
+        int e_cnt;
+        fall_and_refill(e_cnt);                              // ref :362-364 / :374-376
+        elim += e_cnt;
+        pending_fall = false;
+        return true;
+    }
+    __device__ void move_core(int i1, int i2, int& elim_out, int& is_comb) {
+        bool pending_fall = move_begin(i1, i2);
+        is_comb = pending_fall;
+        int elim = 0;
 #pragma unroll 1
-        for (;;) {                                           // ref :367-376
-            if (resolve_round() == 0) break;
-            int e_cnt;
-            fall_and_refill(e_cnt);                          // ref :374-376
-            elim += e_cnt;
-        }
+        while (cascade_trip(pending_fall, elim)) {}
         elim_out = elim + n_new;                             // ref :378 (counters are uniform across lanes)
     }
 
@@ -1611,6 +1626,7 @@ __device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers,
     if (is_step) {
         const int nq = (p.seq & 1) ^ 1;
         p.ctl[CTL_WL_COUNT + nq] = 0u;
+        p.ctl[CTL_WL_COUNT_LO + nq] = 0u;
         p.ctl[CTL_WL_HEAD + nq] = 0u;
     }
     p.ctl[CTL_DONE] = 0u;
@@ -1652,6 +1668,10 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         b.store_cursors();
         if (!(p.flags & FLAG_NO_MASK)) { b.mask_to_smem(effv, effh); b.store_mask(); }
         merge_status(b, p);
+        {
+            const int nsp = min(255, b.radd(__popc(b.last_S)));
+            if (gc.lane == 0) p.n_special[gc.env] = (uint8_t)nsp;
+        }
         write_step_outputs<L>(p, gc.env, gc.lane, 0, 0, 0, 0, 0, 0, 0);
     }
     if (gc.lane == 0) commit_launch(p, (uint32_t)p.N, false);
@@ -1716,17 +1736,24 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
         packed = ((uint32_t)action & IT_ACTION) | (eff ? IT_EFF : 0u) | (regenerate ? IT_REGEN : 0u) |
                  (zero_mask ? IT_ZERO_MASK : 0u) | (from_pool ? IT_FROM_POOL : 0u);
     }
+    const bool hi = heavy && (packed & IT_EFF) && p.n_special[env] >= PRI_SPECIALS;
     TMG_SITE_HERE
-    const unsigned hm = __ballot_sync(0xffffffffu, heavy), rm = __ballot_sync(0xffffffffu, req);
-    uint32_t hbase = 0u, rbase = 0u;
+    const unsigned hm = __ballot_sync(0xffffffffu, hi), lm = __ballot_sync(0xffffffffu, heavy && !hi),
+                   rm = __ballot_sync(0xffffffffu, req);
+    uint32_t hbase = 0u, lbase = 0u, rbase = 0u;
     if (wl == 0) {
         if (hm) hbase = atomicAdd(&p.ctl[CTL_WL_COUNT + q], (uint32_t)__popc(hm));
+        if (lm) lbase = atomicAdd(&p.ctl[CTL_WL_COUNT_LO + q], (uint32_t)__popc(lm));
         if (rm) rbase = atomicAdd(&p.ctl[CTL_REQ_TAIL], (uint32_t)__popc(rm));
     }
     hbase = (uint32_t)__shfl_sync(0xffffffffu, (int)hbase, 0);
+    lbase = (uint32_t)__shfl_sync(0xffffffffu, (int)lbase, 0);
     rbase = (uint32_t)__shfl_sync(0xffffffffu, (int)rbase, 0);
     const unsigned lt = (1u << wl) - 1u;
-    if (heavy) { uint2 it; it.x = (uint32_t)env; it.y = packed; p.wl_items[hbase + (uint32_t)__popc(hm & lt)] = it; }
+    if (heavy) {
+        uint2 it; it.x = (uint32_t)env; it.y = packed;
+        p.wl_items[hi ? hbase + (uint32_t)__popc(hm & lt) : (uint32_t)p.N - 1u - (lbase + (uint32_t)__popc(lm & lt))] = it;
+    }
     if (req) p.req_ring[(rbase + (uint32_t)__popc(rm & lt)) & p.req_mask] = env;
     __syncwarp(0xffffffffu);
     if (wl == 0) commit_launch(p, gridDim.x * (blockDim.x >> 5), true);
@@ -1735,32 +1762,44 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
 #ifndef TMG_STEP_MIN_BLOCKS
 #define TMG_STEP_MIN_BLOCKS 8   // <= 64 registers/thread: 32 warps/SM.  Measured (65 536 envs): 4 blocks 183 M, 6 198 M, 8 228 M, 10 203 M steps/s
 #endif
-// part 2 of a step, for one env of the work list: the move (ref board.py:330-395) and / or the next board
-template <int L, int RT, int CT> __device__ __forceinline__ void step_item(const Params& p, const GroupCtx<L>& gc, int env, uint32_t packed) {
-    const int lane = gc.lane;
-    Board<L, RT, CT> b(group_smem<L>(gc.g), p, lane, gc.gmask, gc.gshift, env);
-    const long long prof_t0 = p.prof ? clock64() : 0;
+// groups of a warp: all done? -- also the point where the groups of the warp reconverge (a __syncwarp over the warp)
+template <int L> __device__ __forceinline__ bool warp_all_done(bool done) {
+#ifdef TMG_EMU
+    return done;               // the emulator runs one group at a time
+#else
+    constexpr unsigned wmask = (Cfg<L>::GPW * L >= 32) ? 0xffffffffu : ((1u << ((Cfg<L>::GPW * L) & 31)) - 1u);
+    return __all_sync(wmask, done);
+#endif
+}
+// next index of a shared cursor for this group, or `n` and above when the list is exhausted
+template <int L> __device__ __forceinline__ uint32_t pop_item(const GroupCtx<L>& gc, uint32_t* head) {
+    uint32_t idx = 0u;
+    TMG_SITE_HERE
+    __syncwarp(gc.gmask);                  // the previous item's shared-memory traffic is complete on every lane
+    if (gc.lane == 0) idx = atomicAdd(head, 1u);
+    return (uint32_t)__shfl_sync(gc.gmask, (int)idx, gc.gshift);
+}
+
+// end of a work-list item: playability (ref board.py:381-391), the next board if the episode ended, state and outputs
+template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Board<L, RT, CT>& b, const Params& p, uint32_t packed,
+                                                                            int elim, int is_comb, long long prof_t0) {
+    const int lane = b.lane, env = b.env;
     const bool want_mask = !(p.flags & FLAG_NO_MASK);
-    const int action = (int)(packed & IT_ACTION);
     const bool eff = packed & IT_EFF, regenerate = packed & IT_REGEN, zero_mask = packed & IT_ZERO_MASK,
                from_pool = packed & IT_FROM_POOL;
     unsigned effv = 0u, effh = 0u;
-    int reward = 0, is_comb = 0, shuffled = 0;
+    int shuffled = 0;
+    const int reward = elim + b.n_new;                                     // ref :378 (counters are uniform across lanes)
+    const int n_new = b.n_new, n_act = b.n_act;
     const int next_ep = regenerate ? p.episode[env] + 1 : 0;
-    b.sync();
     const bool inline_gen = regenerate && !from_pool;
     const bool dirty = eff || inline_gen;
-    if (eff || regenerate) b.load_cursors();
-    // phase 0: the move itself; phase 1: generate_board of the next episode.  One call site each.
+    // phase 0: playability of the moved board; phase 1: generate_board of the next episode.  One call site.
 #pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
         bool clean, all_normal;
         if (phase == 0) {
             if (!eff) continue;
-            b.load_board(p.board, p.board_vecw);
-            int i1, i2;
-            b.action_cells(action, i1, i2);
-            b.move_core(i1, i2, reward, is_comb);
             clean = true; all_normal = false;
         } else {
             if (!inline_gen) continue;
@@ -1771,7 +1810,6 @@ template <int L, int RT, int CT> __device__ __forceinline__ void step_item(const
         if (phase == 0) shuffled = sh;
         else b.end_generate();
     }
-    const int n_new = b.n_new, n_act = b.n_act;
     if (from_pool) {                       // board and mask of the new episode come straight from the pool
         b.sync();
         copy_bytes<L>(p.board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, 2 * p.P, p.board_vecw, lane);
@@ -1795,6 +1833,10 @@ template <int L, int RT, int CT> __device__ __forceinline__ void step_item(const
         }
     }
     merge_status(b, p);
+    if (dirty || from_pool) {              // scheduling hint for the next step: special tiles on the board (a fresh board has none)
+        const int nsp = regenerate ? 0 : min(255, b.radd(__popc(b.last_S)));
+        if (lane == 0) p.n_special[env] = (uint8_t)nsp;
+    }
     if (lane == 0) {
         if (regenerate) p.episode[env] = next_ep;
         if (eff) {                         // k_gate wrote the outputs of a step that changes nothing
@@ -1813,26 +1855,39 @@ template <int L, int RT, int CT> __device__ __forceinline__ void step_item(const
     }
 }
 
-// next index of a shared cursor for this group, or `n` and above when the list is exhausted
-template <int L> __device__ __forceinline__ uint32_t pop_item(const GroupCtx<L>& gc, uint32_t* head) {
-    uint32_t idx = 0u;
-    TMG_SITE_HERE
-    __syncwarp(gc.gmask);                  // the previous item's shared-memory traffic is complete on every lane
-    if (gc.lane == 0) idx = atomicAdd(head, 1u);
-    return (uint32_t)__shfl_sync(gc.gmask, (int)idx, gc.gshift);
-}
-
+// Part 2 of a step: the envs of the work list -- the move (ref board.py:330-395) and / or the next board.
+// Persistent groups pop items until the list is empty: first the items k_gate expects to cascade long (boards rich in
+// special tiles), so that the longest item of the launch runs beside the bulk instead of trailing it.
+// (A warp-level state machine that aligns the cascade rounds of the warp's groups, like k_pregen's loop, was measured
+// no faster here: collectives with a group mask make the groups of a warp separate instruction streams anyway.)
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_work(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
     const int q = p.seq & 1;
-    const uint32_t n = p.ctl[CTL_WL_COUNT + q];
+    const uint32_t n_hi = p.ctl[CTL_WL_COUNT + q], n = n_hi + p.ctl[CTL_WL_COUNT_LO + q];
+    Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, 0);
 #pragma unroll 1
     for (;;) {
         const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_WL_HEAD + q]);
         if (idx >= n) break;
-        const uint2 it = p.wl_items[idx];
-        step_item<L, RT, CT>(p, gc, (int)it.x, it.y);
+        const uint2 it = p.wl_items[idx < n_hi ? idx : (uint32_t)p.N - 1u - (idx - n_hi)];   // high priority from the front, the rest from the back
+        b.rebind((int)it.x);
+        b.prof_serial = 0u; b.prof_rounds = 0u; b.prof_iters = 0u;
+        const uint32_t packed = it.y;
+        const long long prof_t0 = p.prof ? clock64() : 0;
+        int elim = 0, is_comb = 0;
+        b.sync();
+        if (packed & (IT_EFF | IT_REGEN)) b.load_cursors();
+        if (packed & IT_EFF) {
+            b.load_board(p.board, p.board_vecw);
+            int i1, i2;
+            b.action_cells((int)(packed & IT_ACTION), i1, i2);
+            bool pending_fall = b.move_begin(i1, i2);
+            is_comb = pending_fall;
+#pragma unroll 1
+            while (b.cascade_trip(pending_fall, elim)) {}
+        }
+        finish_item<L, RT, CT>(b, p, packed, elim, is_comb, prof_t0);
     }
 }
 
@@ -1935,6 +1990,10 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         if (p.h_board && touched) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, lane);
         if (want_mask && p.T > 0 && (terminal || touched)) b.mirror_mask(terminal);
         merge_status(b, p);
+        if (touched) {
+            const int nsp = min(255, b.radd(__popc(b.last_S)));
+            if (lane == 0) p.n_special[env] = (uint8_t)nsp;
+        }
         if (lane == 0) {
             p.episode[env] = episode;
             if (regenerated && p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = env;   // next board -> pool
@@ -2055,14 +2114,6 @@ template <int BITS> __global__ void __launch_bounds__(128) k_gen_lines(const __g
 // identical scan + redraw iterations, so the groups of a warp are kept CONVERGED: the loop below is one iteration per
 // trip for every group of the warp, with a warp-wide reconvergence point at the top, and a group that finishes its
 // board takes the next request inside the same loop.  One warp instruction then serves all the boards of the warp.
-template <int L> __device__ __forceinline__ bool warp_all_done(bool done) {
-#ifdef TMG_EMU
-    return done;               // the emulator runs one group at a time
-#else
-    constexpr unsigned wmask = (Cfg<L>::GPW * L >= 32) ? 0xffffffffu : ((1u << ((Cfg<L>::GPW * L) & 31)) - 1u);
-    return __all_sync(wmask, done);
-#endif
-}
 template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_pregen(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
