@@ -109,14 +109,14 @@ using namespace tmg;
 
 static Params g_params;
 template <int L> static void e_reset() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_reset<16, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_reset<16, 9, 9>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) k_reset<32, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_reset<32, 9, 9>(g_params);
     else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_reset<32, 32, 32>(g_params);
     else k_reset<L, 0, 0>(g_params);
 }
 template <int L> static void e_step() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_work<16, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_work<16, 9, 9>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) k_work<32, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_work<32, 9, 9>(g_params);
     else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_work<32, 32, 32>(g_params);
     else k_work<L, 0, 0>(g_params);
 }
@@ -134,14 +134,14 @@ static void launch_threads(void (*fn)(), int n) {
     }
 }
 template <int L> static void e_pregen() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_pregen<16, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_pregen<16, 9, 9>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) k_pregen<32, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_pregen<32, 9, 9>(g_params);
     else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_pregen<32, 32, 32>(g_params);
     else k_pregen<L, 0, 0>(g_params);
 }
 template <int L> static void e_rollout() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 16) k_rollout<16, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 16) k_rollout<16, 9, 9>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) k_rollout<32, 10, 10>(g_params);
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_rollout<32, 9, 9>(g_params);
     else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_rollout<32, 32, 32>(g_params);
     else k_rollout<L, 0, 0>(g_params);
 }
@@ -193,10 +193,11 @@ void* emu_create(const emu_config* c) {
     p.max_iters = c->max_reset_iters > 0 ? c->max_reset_iters : 16384;
     p.key0 = (uint32_t)c->seed; p.key1 = (uint32_t)(c->seed >> 32); p.env_id_offset = c->env_id_offset;
     p.board_vecw = vec_width((size_t)2 * p.P); p.mask_vecw = vec_width((size_t)p.A); p.init_vecw = 1;
-    // 10x10 / 9x9 run the fixed-shape 16-lane kernels (as the library does); other 9/10-column shapes keep the 10-lane
-    // groups covered in the emulator
+    // 10x10 / 9x9 / 32x32 run the fixed-shape one-board-per-warp kernels (as the library does); the other shapes keep
+    // the sub-warp groups (8, 10, 16 lanes; the library's TMG_B200_LANES knob) covered in the emulator
     const bool fixed = (p.R == 10 && p.C == 10) || (p.R == 9 && p.C == 9);
-    e->L = (p.R > 16) ? 32 : (p.C <= 8 ? 8 : ((p.C <= 10 && !fixed) ? 10 : (p.C <= 16 ? 16 : 32)));
+    e->L = (p.R > 16 || fixed) ? 32 : (p.C <= 8 ? 8 : (p.C <= 10 ? 10 : (p.C <= 16 ? 16 : 32)));
+    if (getenv("TMG_EMU_LANES32")) e->L = 32;
     const size_t N = (size_t)p.N;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };

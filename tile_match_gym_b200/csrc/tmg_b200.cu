@@ -62,17 +62,11 @@ template <int L_, int R_, int C_> struct Shape { static constexpr int L = L_, R 
 template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
     const int R = e->p.R, C = e->p.C;
     static const bool generic_only = getenv("TMG_B200_GENERIC_SHAPES") != nullptr;   // diagnostics: skip the fixed-shape kernels
-    if (generic_only || e->L == 10) {
-        switch (e->L) {
-            case 8: return f(Shape<8, 0, 0>());
-            case 10: return f(Shape<10, 0, 0>());
-            case 16: return f(Shape<16, 0, 0>());
-            default: return f(Shape<32, 0, 0>());
-        }
+    if (e->L == 32 && !generic_only) {
+        if (R == 10 && C == 10) return f(Shape<32, 10, 10>());
+        if (R == 9 && C == 9) return f(Shape<32, 9, 9>());
+        if (R == 32 && C == 32) return f(Shape<32, 32, 32>());
     }
-    if (R == 10 && C == 10) return f(Shape<16, 10, 10>());
-    if (R == 9 && C == 9) return f(Shape<16, 9, 9>());
-    if (R == 32 && C == 32) return f(Shape<32, 32, 32>());
     switch (e->L) {
         case 8: return f(Shape<8, 0, 0>());
         case 10: return f(Shape<10, 0, 0>());
@@ -202,11 +196,17 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     tmg_env* e = new (std::nothrow) tmg_env();
     if (!e) return TMG_ERR_OOM;
     e->cfg = *cfg;
-    // lanes per board.  10-lane groups (three 9/10-column boards per warp) are supported by the kernels but measured no
-    // faster than 16-lane groups on B200: groups of a warp diverge, so a warp instruction serves one group either way,
-    // and the spare lanes of a 16-lane group compute Philox blocks.  TMG_B200_LANES10=1 selects them for experiments.
-    static const bool lanes10 = getenv("TMG_B200_LANES10") != nullptr;
-    e->L = (R > 16) ? 32 : (C <= 8 ? 8 : ((C <= 10 && lanes10) ? 10 : (C <= 16 ? 16 : 32)));
+    // Lanes per board: ONE BOARD PER WARP (lane c owns column c, the other lanes help with Philox blocks and copies).
+    // Sub-warp groups (2-4 boards per warp) are supported by the same code and were the first design, but measured
+    // slower on B200 at every batch size up to 262 144 envs (65 536 envs: 232 M vs 253 M steps/s; 1 024 envs: 8.6 M vs
+    // 11.5 M): the groups of a warp diverge into separate instruction streams anyway, their collectives need a
+    // runtime membership check, and the step is bound by instruction supply, not by lanes.  TMG_B200_LANES=8|10|16
+    // selects them (runtime-shape kernels) for experiments.
+    e->L = 32;
+    if (const char* lanes = getenv("TMG_B200_LANES")) {
+        const int l = atoi(lanes);
+        if ((l == 8 && C <= 8 && R <= 16) || (l == 10 && C <= 10 && R <= 16) || (l == 16 && C <= 16 && R <= 16)) e->L = l;
+    }
     e->planes = tmg_onehot_planes(K, cfg->specials);
     Params& p = e->p;
     memset(&p, 0, sizeof(p));

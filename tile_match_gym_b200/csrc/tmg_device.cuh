@@ -366,25 +366,28 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     }
 
     // ---- group collectives ---------------------------------------------------------------------------
-    __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return (__ballot_sync(gmask, pr) >> gshift) & CF::LMASK; }
-    __device__ __forceinline__ void sync(TMG_SITE_P0) const { TMG_SITE_SET __syncwarp(gmask); }
+    // a 32-lane group is the whole warp: a literal full mask lets the compiler emit the collectives without the
+    // runtime membership check (MATCH.ANY / REDUX / VOTEU + divergent-path trampoline) a group mask in a register needs
+    __device__ __forceinline__ unsigned gm() const { return L == 32 ? 0xffffffffu : gmask; }
+    __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return L == 32 ? __ballot_sync(0xffffffffu, pr) : ((__ballot_sync(gmask, pr) >> gshift) & CF::LMASK); }
+    __device__ __forceinline__ void sync(TMG_SITE_P0) const { TMG_SITE_SET __syncwarp(gm()); }
     // groups need not be a power of two wide (10-lane groups: three 10-column boards per warp), so shuffles address
     // absolute lanes of the warp
-    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gmask, v, gshift + src); }
-    __device__ __forceinline__ int radd(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_add_sync(gmask, v); }
-    __device__ __forceinline__ int rmax(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_max_sync(gmask, v); }
-    __device__ __forceinline__ int rmin(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_min_sync(gmask, v); }
-    __device__ __forceinline__ unsigned ror(unsigned v TMG_SITE_P) const { TMG_SITE_SET return __reduce_or_sync(gmask, v); }
+    __device__ __forceinline__ int shfl(int v, int src TMG_SITE_P) const { TMG_SITE_SET return __shfl_sync(gm(), v, (L == 32 ? 0 : gshift) + src); }
+    __device__ __forceinline__ int radd(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_add_sync(gm(), v); }
+    __device__ __forceinline__ int rmax(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_max_sync(gm(), v); }
+    __device__ __forceinline__ int rmin(int v TMG_SITE_P) const { TMG_SITE_SET return __reduce_min_sync(gm(), v); }
+    __device__ __forceinline__ unsigned ror(unsigned v TMG_SITE_P) const { TMG_SITE_SET return __reduce_or_sync(gm(), v); }
     __device__ __forceinline__ unsigned lt_mask() const { return (1u << lane) - 1u; }
     // neighbour-lane bitboards: value of lane+d / lane-d, 0 outside [0,L)
     __device__ __forceinline__ unsigned from_right(unsigned v, int d TMG_SITE_P) const {
         TMG_SITE_SET
-        const unsigned r = __shfl_down_sync(gmask, v, d);
+        const unsigned r = __shfl_down_sync(gm(), v, d);
         return (lane + d < L) ? r : 0u;
     }
     __device__ __forceinline__ unsigned from_left(unsigned v, int d TMG_SITE_P) const {
         TMG_SITE_SET
-        const unsigned r = __shfl_up_sync(gmask, v, d);
+        const unsigned r = __shfl_up_sync(gm(), v, d);
         return (lane - d >= 0) ? r : 0u;
     }
     __device__ __forceinline__ unsigned rows_mask() const { return R >= 32 ? 0xffffffffu : ((1u << R) - 1u); }
@@ -1775,9 +1778,10 @@ template <int L> __device__ __forceinline__ bool warp_all_done(bool done) {
 template <int L> __device__ __forceinline__ uint32_t pop_item(const GroupCtx<L>& gc, uint32_t* head) {
     uint32_t idx = 0u;
     TMG_SITE_HERE
-    __syncwarp(gc.gmask);                  // the previous item's shared-memory traffic is complete on every lane
+    const unsigned gm = L == 32 ? 0xffffffffu : gc.gmask;
+    __syncwarp(gm);                        // the previous item's shared-memory traffic is complete on every lane
     if (gc.lane == 0) idx = atomicAdd(head, 1u);
-    return (uint32_t)__shfl_sync(gc.gmask, (int)idx, gc.gshift);
+    return (uint32_t)__shfl_sync(gm, (int)idx, L == 32 ? 0 : gc.gshift);
 }
 
 // end of a work-list item: playability (ref board.py:381-391), the next board if the episode ended, state and outputs
