@@ -312,6 +312,50 @@ def test_step_many_equals_single_steps(R, Cc, K, moves, autoreset, T):
         assert_same(g, o, f"single step after window {window}")
 
 
+def test_checkpoint_resume_reproduces_the_trajectory():
+    """state_dict / load_state_dict: an env resumed from a checkpoint -- the same handle or a fresh one --
+    continues bit for bit like the original, including the boards of later episodes and a bound host mirror."""
+    torch = _torch()
+    N, R, Cc, K, moves = 2000, 10, 10, 4, 6
+    mk = lambda: make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=12, autoreset="same_step", env_id_offset=100)  # noqa: E731
+    env = mk()
+    env.reset()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    acts = [torch.randint(0, env.num_actions, (N,), device="cuda", dtype=torch.int32, generator=gen) for _ in range(30)]
+    for a in acts[:9]:
+        env.step(a)
+    sd = env.state_dict()
+    want = []
+    for a in acts[9:]:
+        _, rew, term, _, _ = env.step(a)
+        want.append((env.board.cpu().clone(), rew.cpu().clone(), term.cpu().clone(), env.mask.cpu().clone()))
+    fresh = mk()
+    for e in (env, fresh):
+        e.load_state_dict(sd)
+        for a, (wb, wr, wt, wm) in zip(acts[9:], want):
+            _, rew, term, _, _ = e.step(a)
+            assert torch.equal(e.board.cpu(), wb) and torch.equal(rew.cpu(), wr) and torch.equal(term.cpu(), wt)
+            assert torch.equal(e.mask.cpu(), wm)
+        assert int((e.status != 0).sum().item()) == 0
+
+
+def test_proportion_reward_wrapper():
+    """ProportionRewardWrapper (wrappers.py:71-77): reward / (rows * cols) as the reference's float."""
+    from tile_match_gym_b200 import ProportionRewardWrapper
+    N, R, Cc, K, moves = 512, 9, 9, 6, 12
+    env = ProportionRewardWrapper(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=3, autoreset="same_step"))
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=3, autoreset="same_step", num_threads=4)
+    env.reset(); o.reset()
+    rng = np.random.default_rng(4)
+    for t in range(15):
+        m = o.mask.astype(np.float64) + 1e-9
+        u = rng.random((N, 1)) * m.sum(axis=1, keepdims=True)
+        a = (np.cumsum(m, axis=1) < u).sum(axis=1).clip(0, o.A - 1).astype(np.int32)
+        _, rew, _, _, _ = env.step(_torch().from_numpy(a).cuda()); o.step(a)
+        want = np.array([float(int(r) / (R * Cc)) for r in o.reward])      # the reference: reward / self.flat_size
+        assert rew.dtype == _torch().float64 and np.array_equal(rew.cpu().numpy(), want)
+
+
 def test_reset_with_seed_and_partial_reset():
     torch = _torch()
     N, R, Cc, K, moves = 600, 6, 6, 4, 50

@@ -181,6 +181,34 @@ class TileMatchVecEnv:
         self.seed = int(seed)
         nat.check(self._lib.tmg_set_seed(self._h, self.seed & 0xFFFFFFFFFFFFFFFF, self._stream()), "tmg_set_seed")
 
+    # ---- checkpoint / resume: the state of an env is its board, timer, stream cursors and episode number
+    STATE_FIELDS = ("board", "timer", "draw_cursor", "shuffle_cursor", "episode", "num_moves_left", "status", "reward",
+                    "terminated", "is_combination_match", "num_new_specials", "num_specials_activated", "shuffled")
+
+    def state_dict(self) -> dict:
+        """Host copy of everything the next steps depend on (boards generated ahead of time are not state: board j of
+        env e is a pure function of (seed, e, j))."""
+        self.join()
+        torch.cuda.synchronize(self.device)
+        sd = {name: self._t[name].detach().cpu().clone() for name in self.STATE_FIELDS}
+        sd["config"] = {"seed": self.seed, "num_envs": self.num_envs, "num_rows": self.num_rows, "num_cols": self.num_cols,
+                        "num_colours": self.num_colours, "num_moves": self.num_moves, "specials": self.specials,
+                        "env_id_offset": self.env_id_offset}
+        return sd
+
+    def load_state_dict(self, sd: dict) -> None:
+        """Resume from state_dict(): the following steps reproduce, bit for bit, what the saved env would have done."""
+        cfg = sd["config"]
+        for k in ("num_envs", "num_rows", "num_cols", "num_colours", "num_moves", "specials", "env_id_offset"):
+            if cfg[k] != getattr(self, k):
+                raise ValueError(f"state was saved with {k}={cfg[k]}, this env has {getattr(self, k)}")
+        if cfg["seed"] != self.seed:
+            self.set_seed(cfg["seed"])       # also forgets the boards generated ahead of time under the old key
+        self.join()
+        for name in self.STATE_FIELDS:
+            self._t[name].copy_(sd[name].to(self._t[name].dtype))
+        self.legal_mask()                    # masks (and a bound host mirror) follow from the boards
+
     def set_injected_draws(self, draws: torch.Tensor) -> None:
         """draws: (N, Ldraws) uint8 on this device, values 1..K; consumed in the reference's draw order."""
         if self.refill != "injected":
@@ -317,6 +345,34 @@ class TileMatchVecEnv:
             lines.append("| " + " ".join(f"{b[0, r, c]}{'*' if b[1, r, c] not in (0, 1) else ''}" for c in range(self.num_cols)) + " |")
         lines.append(" " + "-" * (self.num_cols * 2 + 1))
         print("\n".join(lines))
+
+
+class ProportionRewardWrapper:
+    """wrappers.py:71-77 for the vector env: reward / (num_rows * num_cols), float64 like the reference's Python
+    float (int / int).  Everything else is forwarded to the wrapped TileMatchVecEnv."""
+
+    def __init__(self, env: TileMatchVecEnv):
+        self.env = env
+        self.flat_size = env.num_rows * env.num_cols
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reward(self, reward: torch.Tensor) -> torch.Tensor:
+        # tensor / tensor is an IEEE division; tensor / python-scalar is a multiplication by the reciprocal on CUDA,
+        # which differs from the reference's int / int in the last bit
+        return reward.to(torch.float64) / torch.full((), float(self.flat_size), dtype=torch.float64, device=reward.device)
+
+    def reset(self, **kw):
+        return self.env.reset(**kw)
+
+    def step(self, actions):
+        obs, reward, terminated, truncated, info = self.env.step(actions)
+        return obs, self.reward(reward), terminated, truncated, info
+
+    def step_many(self, actions):
+        rewards, terminated = self.env.step_many(actions)
+        return self.reward(rewards), terminated
 
 
 class HostStepper:
