@@ -196,15 +196,18 @@ typedef struct tmg_host_io {
 } tmg_host_io;
 int tmg_step_host(tmg_env *env, const tmg_host_io *io, void *stream);
 
-/* Host mirror: the fast form of the host-buffer path.  Registers page-locked host arrays (cudaHostAlloc /
- * cudaHostRegister memory, 16-byte aligned; any of them may be NULL) as a mirror of buffers.board / buffers.mask /
- * the bit-packed mask.  The call copies the current contents in full; from then on tmg_step's kernel writes the
- * entries of exactly those envs whose board or mask it changed straight into the arrays over PCIe (a step that
- * changes nothing moves no board bytes), and tmg_reset / tmg_legal_mask / tmg_debug_op re-copy them in full.
- * The arrays are complete and current whenever the stream work of the last call has finished -- the reference's
- * obs["board"] aliases live state the same way (tile_match_env.py:115).  tmg_step_host skips the copies of output
- * pointers that are the bound arrays.  All NULL unbinds.  Returns TMG_ERR_INVALID_ARG for pageable memory. */
-int tmg_host_bind(tmg_env *env, int8_t *board_host, uint8_t *mask_host, uint8_t *mask_bits_host, void *stream);
+/* Host mirror: the fast form of the host-buffer path.  Registers the page-locked host arrays of `io` (cudaHostAlloc /
+ * cudaHostRegister memory, 16-byte aligned; any of them may be NULL) as a mirror of buffers.board / buffers.mask / the
+ * bit-packed mask / reward / terminated / num_moves_left.  The
+ * call copies the current contents in full; from then on tmg_step's kernels write, straight into the arrays over PCIe,
+ * the board and mask entries of exactly those envs whose board or mask they changed (a step that changes nothing moves
+ * no board bytes) and the three per-env scalars of every env (coalesced), and tmg_reset / tmg_legal_mask /
+ * tmg_debug_op re-copy them in full.  The arrays are complete and current whenever the stream work of the last call
+ * has finished -- the reference's obs["board"] aliases live state the same way (tile_match_env.py:115).
+ * tmg_step_host skips the copies of pointers that are the bound arrays and, while a mirror is bound, reads page-locked
+ * actions in place instead of staging them.  The other fields of `io` are ignored;
+ * io == NULL unbinds.  Returns TMG_ERR_INVALID_ARG for pageable memory. */
+int tmg_host_bind(tmg_env *env, const tmg_host_io *io, void *stream);
 
 /* Debug / known-answer entry point: runs ONE engine primitive on every env's device board, so that the
  * reference's function-level tests (tests/board/*.py) can be replayed on the GPU.  args_dev: int32 [N][4].

@@ -47,7 +47,7 @@ def lib():
         L.emu_create.argtypes = [C.POINTER(_Cfg)]
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_get_buffers.argtypes = [C.c_void_p, C.POINTER(_Bufs)]
-        L.emu_host_bind.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emu_host_bind.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         L.emu_set_injected_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.emu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_void_p]
@@ -102,7 +102,10 @@ class EmuVecEnv:
         self.h_board = self.board.copy()
         self.h_mask = self.mask.copy()
         self.h_mask_bits = np.packbits(self.mask, axis=1, bitorder="little")[:, :bpe].copy()
-        self.L.emu_host_bind(self.h, _ptr(self.h_board), _ptr(self.h_mask), _ptr(self.h_mask_bits))
+        self.h_reward = self.reward.copy(); self.h_terminated = self.terminated.copy()
+        self.h_moves_left = self.num_moves_left.copy()
+        self.L.emu_host_bind(self.h, _ptr(self.h_board), _ptr(self.h_mask), _ptr(self.h_mask_bits), _ptr(self.h_reward),
+                             _ptr(self.h_terminated), _ptr(self.h_moves_left))
 
     def reset(self, reset_mask=None, init_boards=None):
         m = None if reset_mask is None else np.ascontiguousarray(reset_mask, dtype=np.uint8)

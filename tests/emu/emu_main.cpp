@@ -236,9 +236,11 @@ void emu_get_buffers(void* h, emu_buffers* o) {
     o->num_new_specials = p.new_specials; o->num_specials_activated = p.activated; o->shuffled = p.shuffled;
     o->mask = p.mask; o->num_moves_left = p.moves_left; o->status = p.status; o->episode = p.episode;
 }
-void emu_host_bind(void* h, int8_t* board, uint8_t* mask, uint8_t* mask_bits) {   // the mirror is ordinary memory here
+void emu_host_bind(void* h, int8_t* board, uint8_t* mask, uint8_t* mask_bits, int32_t* reward, uint8_t* terminated,
+                   int32_t* moves_left) {   // the mirror is ordinary memory here
     Params& p = ((EmuEnv*)h)->p;
     p.h_board = board; p.h_mask = mask; p.h_mask_bits = mask_bits;
+    p.h_reward = reward; p.h_terminated = terminated; p.h_moves_left = moves_left;
 }
 void emu_set_injected_draws(void* h, const uint8_t* d, int64_t len) { ((EmuEnv*)h)->p.inj = d; ((EmuEnv*)h)->p.inj_len = len; }
 

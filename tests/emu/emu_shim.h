@@ -85,6 +85,11 @@ template <typename T> static inline T __shfl_up_sync(unsigned mask, T val, int d
     const int idx = (me - base) - d;
     return (T)(uint32_t)v[idx >= 0 ? base + idx : me];
 }
+template <typename T> static inline T __shfl_xor_sync(unsigned mask, T val, int lanemask, int width = 32) {
+    const uint64_t* v = emu::gather((uint64_t)(uint32_t)val, mask);
+    const int me = emu::cur->lane_in_warp;
+    return (T)(uint32_t)v[(me ^ lanemask) & 31];
+}
 static inline int __reduce_add_sync(unsigned mask, int val) {
     const uint64_t* v = emu::gather((uint64_t)(uint32_t)val, mask);
     int s = 0;

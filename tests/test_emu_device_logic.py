@@ -70,6 +70,8 @@ def test_emulated_step_many_equals_single_steps(R, C, K, moves, autoreset, T):
         for f in fields:
             assert np.array_equal(getattr(e, f), getattr(o, f)), (window, f)
         assert np.array_equal(e.h_board, e.board) and np.array_equal(e.h_mask, e.mask)
+        assert np.array_equal(e.h_reward, e.reward) and np.array_equal(e.h_terminated, e.terminated)
+        assert np.array_equal(e.h_moves_left, e.num_moves_left)
         e.step(acts[0]); o.step(acts[0])      # single steps and rollouts interleave
         for f in fields:
             assert np.array_equal(getattr(e, f), getattr(o, f)), (window, "after single step", f)
@@ -107,6 +109,8 @@ def test_emulated_host_mirror_tracks_device_state(R, C, K, moves, autoreset):
         assert np.array_equal(e.h_board, e.board), t
         assert np.array_equal(e.h_mask, e.mask), t
         assert np.array_equal(e.h_mask_bits, np.packbits(e.mask, axis=1, bitorder="little")), t
+        assert np.array_equal(e.h_reward, e.reward) and np.array_equal(e.h_terminated, e.terminated), t
+        assert np.array_equal(e.h_moves_left, e.num_moves_left), t
 
 
 # ----------------------------------------------------------------------------------------------

@@ -273,7 +273,9 @@ def test_host_mirror_write_through_matches_oracle(autoreset, R, Cc, K):
     # pageable memory is refused, not silently staged
     import ctypes as C
     bad = np.zeros((N, 2, R, Cc), np.int8)
-    assert env._lib.tmg_host_bind(env._h, C.c_void_p(bad.ctypes.data), None, None, env._stream()) != 0
+    from tile_match_gym_b200 import _native as nat
+    io = nat.HostIO(); io.board = bad.ctypes.data
+    assert env._lib.tmg_host_bind(env._h, C.byref(io), env._stream()) != 0
 
 
 @pytest.mark.parametrize("R,Cc,K,moves,autoreset,T", [(10, 10, 4, 30, "same_step", 30), (10, 10, 4, 7, "same_step", 20),

@@ -77,7 +77,7 @@ EXPORTS = {
     "tmg_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "tmg_step_host": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_void_p]),
-    "tmg_host_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_host_bind": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_void_p]),
     "tmg_set_profile_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_debug_op": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
 }

@@ -34,7 +34,9 @@ struct tmg_env {
     bool pregen;              // pool in use (philox refill, not disabled by flag)
     // host mirror (tmg_host_bind): the caller's page-locked arrays; p.h_* are their device-visible aliases
     int8_t* hm_board;
-    uint8_t *hm_mask, *hm_mask_bits;
+    uint8_t *hm_mask, *hm_mask_bits, *hm_terminated;
+    int32_t *hm_reward, *hm_moves_left;
+    bool hm_bound;                  // any array bound: tmg_step_host then also reads page-locked actions in place
 };
 
 namespace {
@@ -271,7 +273,8 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
     e->step_count = 0;
-    e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr;
+    e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr; e->hm_terminated = nullptr;
+    e->hm_reward = nullptr; e->hm_moves_left = nullptr; e->hm_bound = false;
     p.req_ring = e->pregen ? reinterpret_cast<int32_t*>(b + o_ring) : nullptr;
     // Thread-per-board first stage of the pool refill (k_gen_lines): boards whose rows fit one 32-bit word of 2- or 3-bit
     // cells.  EXPERIMENT, opt-in (TMG_B200_GEN_LINES=1): bit-exact, but measured no faster than the group kernel at 65 536
@@ -361,25 +364,37 @@ static int refresh_mirror(tmg_env* e, cudaStream_t st) {
         ok &= cudaGetLastError() == cudaSuccess;
         ok &= cudaMemcpyAsync(e->hm_mask_bits, e->mask_bits_dev, (size_t)total, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     }
+    if (e->hm_reward) ok &= cudaMemcpyAsync(e->hm_reward, p.reward, N * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (e->hm_terminated) ok &= cudaMemcpyAsync(e->hm_terminated, p.terminated, N, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (e->hm_moves_left) ok &= cudaMemcpyAsync(e->hm_moves_left, p.moves_left, N * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     return ok ? TMG_OK : TMG_ERR_CUDA;
 }
 
-int tmg_host_bind(tmg_env* e, int8_t* board_host, uint8_t* mask_host, uint8_t* mask_bits_host, void* stream) {
+int tmg_host_bind(tmg_env* e, const tmg_host_io* io, void* stream) {
     if (!e) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
-    void* dev[3] = {nullptr, nullptr, nullptr};
-    void* host[3] = {board_host, mask_host, mask_bits_host};
-    for (int i = 0; i < 3; ++i) {
+    static const tmg_host_io none = {};
+    if (!io) io = &none;
+    void* host[6] = {io->board, io->mask, io->mask_bits, io->reward, io->terminated, io->num_moves_left};
+    void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool any = false;
+    for (int i = 0; i < 6; ++i) {
         if (!host[i]) continue;
         if (reinterpret_cast<uintptr_t>(host[i]) % 16 != 0) return TMG_ERR_INVALID_ARG;
-        // page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) memory only: the kernels write it directly
+        // page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) memory only: the kernels access it directly
         if (cudaHostGetDevicePointer(&dev[i], host[i], 0) != cudaSuccess) { cudaGetLastError(); return TMG_ERR_INVALID_ARG; }
+        any = true;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    e->hm_board = board_host; e->hm_mask = mask_host; e->hm_mask_bits = mask_bits_host;
+    e->hm_bound = any;
+    e->hm_board = io->board; e->hm_mask = io->mask; e->hm_mask_bits = io->mask_bits;
+    e->hm_reward = io->reward; e->hm_terminated = io->terminated; e->hm_moves_left = io->num_moves_left;
     e->p.h_board = static_cast<int8_t*>(dev[0]);
     e->p.h_mask = static_cast<uint8_t*>(dev[1]);
     e->p.h_mask_bits = static_cast<uint8_t*>(dev[2]);
+    e->p.h_reward = static_cast<int32_t*>(dev[3]);
+    e->p.h_terminated = static_cast<uint8_t*>(dev[4]);
+    e->p.h_moves_left = static_cast<int32_t*>(dev[5]);
     return refresh_mirror(e, st);
 }
 
@@ -522,8 +537,18 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const Params& p = e->p;
     const size_t N = (size_t)p.N;
-    if (cudaMemcpyAsync(e->actions_dev, io->actions, N * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return TMG_ERR_CUDA;
-    const int rc = tmg_step(e, e->actions_dev, stream);
+    // With a host mirror bound, actions in page-locked memory are read in place by k_gate (one coalesced PCIe read per
+    // warp) instead of being staged by a copy; pageable actions are staged as usual.
+    const int32_t* actions = e->actions_dev;
+    void* in_place = nullptr;
+    if (e->hm_bound && reinterpret_cast<uintptr_t>(io->actions) % 4 == 0 &&
+        cudaHostGetDevicePointer(&in_place, const_cast<int32_t*>(io->actions), 0) == cudaSuccess && in_place) {
+        actions = static_cast<const int32_t*>(in_place);
+    } else {
+        cudaGetLastError();
+        if (cudaMemcpyAsync(e->actions_dev, io->actions, N * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return TMG_ERR_CUDA;
+    }
+    const int rc = tmg_step(e, actions, stream);
     if (rc != TMG_OK) return rc;
     bool ok = true;
     auto back = [&](void* dst, const void* src, size_t bytes) {
@@ -531,8 +556,8 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     };
     // arrays bound as the host mirror were already updated in place by the step kernel
     if (io->board != e->hm_board) back(io->board, p.board, N * 2 * p.P);
-    back(io->reward, p.reward, N * 4);
-    back(io->terminated, p.terminated, N);
+    if (io->reward != e->hm_reward) back(io->reward, p.reward, N * 4);
+    if (io->terminated != e->hm_terminated) back(io->terminated, p.terminated, N);
     if (io->mask != e->hm_mask) back(io->mask, p.mask, N * p.A);
     if (io->mask_bits && io->mask_bits != e->hm_mask_bits) {
         const int bpe = (p.A + 7) / 8;
@@ -541,7 +566,7 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
         ok &= cudaGetLastError() == cudaSuccess;
         back(io->mask_bits, e->mask_bits_dev, (size_t)total);
     }
-    back(io->num_moves_left, p.moves_left, N * 4);
+    if (io->num_moves_left != e->hm_moves_left) back(io->num_moves_left, p.moves_left, N * 4);
     back(io->is_combination_match, p.is_comb, N);
     back(io->num_new_specials, p.new_specials, N * 4);
     back(io->num_specials_activated, p.activated, N * 4);

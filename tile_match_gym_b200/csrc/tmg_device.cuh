@@ -107,6 +107,9 @@ struct Params {
     int8_t* h_board;         // [N][2][R][C]
     uint8_t* h_mask;         // [N][A]
     uint8_t* h_mask_bits;    // [N][(A+7)/8]  bit j of byte b = action 8b + j
+    int32_t* h_reward;       // [N]  per-env scalars: k_gate writes them coalesced, the workers overwrite the reward of a move
+    uint8_t* h_terminated;   // [N]
+    int32_t* h_moves_left;   // [N]
     // per-call inputs
     const int32_t* actions;
     const uint8_t* reset_mask;
@@ -242,6 +245,25 @@ template <int L> __device__ __forceinline__ void zero_bytes(void* dst, int nbyte
     }
 }
 
+// compile-time sized copy for the fixed board shapes: no call, no loop, the widest vector the size allows
+template <int W> struct VecOf { typedef uint8_t T; };
+template <> struct VecOf<2> { typedef uint16_t T; };
+template <> struct VecOf<4> { typedef uint32_t T; };
+template <> struct VecOf<8> { typedef uint2 T; };
+template <> struct VecOf<16> { typedef uint4 T; };
+__host__ __device__ constexpr int vecw_of(int nbytes) { return nbytes % 16 == 0 ? 16 : nbytes % 8 == 0 ? 8 : nbytes % 4 == 0 ? 4 : nbytes % 2 == 0 ? 2 : 1; }
+template <int L, int NBYTES> __device__ __forceinline__ void copy_fixed(void* dst, const void* src, int lane) {
+    constexpr int W = vecw_of(NBYTES), n = NBYTES / W;
+    typedef typename VecOf<W>::T V;
+    V* d = reinterpret_cast<V*>(dst);
+    const V* s = reinterpret_cast<const V*>(src);
+#pragma unroll
+    for (int i = 0; i < (n + L - 1) / L; ++i) {
+        const int k = lane + i * L;
+        if (k < n) d[k] = s[k];
+    }
+}
+
 // k-th pre-drawn colour of an env in injected mode, -1 when the stream is exhausted
 __device__ __noinline__ int injected_draw(const uint8_t* inj, long long inj_len, int env, long long q) {
     if (q < inj_len) return inj[(size_t)env * (size_t)inj_len + (size_t)q];
@@ -343,6 +365,11 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     uint32_t gid;
     uint32_t status;
     int n_new, n_act;  // counters, uniform after broadcast (ref :343-344)
+    // Deferred deletions of a fast-path round: the cells [fg_top, fg_top + fg_len) of this lane's column.  They are not
+    // zeroed -- fall_and_refill shifts the rows above them down over them and refills the top (fixed small shapes only).
+    int fg_top = 0, fg_len = 0;
+    bool fg_valid = false;
+    static constexpr bool DEFER_GAPS = TMG_FUSED_FALL && RT > 0 && RT <= 16;
     unsigned last_S = 0u;  // special tiles of this lane's column as of the last mask_bits (scheduling hint, see n_special)
     uint32_t prof_serial = 0u, prof_rounds = 0u, prof_iters = 0u;  // diagnostics (written only when p.prof is set)
     const uint32_t specials;   // copies of the Params fields the round code needs (no pointer chasing out of line)
@@ -392,25 +419,36 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     }
     __device__ __forceinline__ unsigned rows_mask() const { return R >= 32 ? 0xffffffffu : ((1u << R) - 1u); }
 
+    // ---- board / mask sized copies (compile-time size for the fixed shapes) ------------------------------------
+    static constexpr int NB_FIXED = RT ? 2 * RT * CT : 1, NA_FIXED = RT ? 2 * RT * CT - RT - CT : 1;
+    __device__ __forceinline__ void copy_board(void* dst, const void* src, int vecw) const {
+        if (RT && vecw == vecw_of(NB_FIXED)) copy_fixed<L, NB_FIXED>(dst, src, lane);
+        else copy_bytes<L>(dst, src, 2 * P, vecw, lane);
+    }
+    __device__ __forceinline__ void copy_mask(void* dst, const void* src) const {
+        if (RT && p.mask_vecw == vecw_of(NA_FIXED)) copy_fixed<L, NA_FIXED>(dst, src, lane);
+        else copy_bytes<L>(dst, src, p.A, p.mask_vecw, lane);
+    }
+
     // ---- state I/O -----------------------------------------------------------------------------------
     __device__ __forceinline__ void load_board(const int8_t* src, int vecw) {
-        copy_bytes<L>(s.board, src + (size_t)env * 2 * P, 2 * P, vecw, lane);
+        copy_board(s.board, src + (size_t)env * 2 * P, vecw);
         sync();
     }
     __device__ __forceinline__ void store_board() {
         sync();
-        copy_bytes<L>(p.board + (size_t)env * 2 * P, s.board, 2 * P, p.board_vecw, lane);
+        copy_board(p.board + (size_t)env * 2 * P, s.board, p.board_vecw);
     }
     __device__ __forceinline__ void store_mask() {
         sync();
-        copy_bytes<L>(p.mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
+        copy_mask(p.mask + (size_t)env * p.A, s.mask);
     }
     __device__ __forceinline__ void store_zero_mask() { zero_bytes<L>(p.mask + (size_t)env * p.A, p.A, p.mask_vecw, lane); }
     // host mirror: this env's mask (s.mask, or all zero) as bytes and / or bits, straight into page-locked host memory
     __device__ __forceinline__ void mirror_mask(bool zero) {
         if (p.h_mask) {
             if (zero) zero_bytes<L>(p.h_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
-            else copy_bytes<L>(p.h_mask + (size_t)env * p.A, s.mask, p.A, p.mask_vecw, lane);
+            else copy_mask(p.h_mask + (size_t)env * p.A, s.mask);
         }
         if (p.h_mask_bits) {
             const int bpe = (p.A + 7) >> 3;
@@ -560,29 +598,46 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             const uint64_t b = b0 + (uint64_t)lane;
             philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, 0u, p.key0, p.key1, w);
         }
-        int x[RR], t[RR];
-        unsigned empt = 0u, tz = 0u;
-        if (lane < C) {
-#pragma unroll
-            for (int r = 0; r < RR; ++r) {
-                x[r] = col[r * C + lane];
-                t[r] = typ[r * C + lane];
-                empt |= (unsigned)(x[r] == 0 && t[r] == 0) << r;
-                tz |= (unsigned)(t[r] == 0) << r;
+        int e;
+        if (fg_valid) {
+            // after a fast-path round every column has at most one gap and the round knows it: shift the rows above it down
+            fg_valid = false;
+            const int len = fg_len, top = fg_top;
+            const int mt = rmax(len ? top : 0);
+#pragma unroll 1
+            for (int r = mt - 1; r >= 0; --r) {
+                if (len && r < top) {
+                    col[(r + len) * C + lane] = col[r * C + lane];
+                    typ[(r + len) * C + lane] = typ[r * C + lane];
+                }
             }
-            if (empt) {
+            e = len;
+            elim_add = radd(len);                                  // ref :374: the deleted cells are the type-0 cells
+        } else {
+            int x[RR], t[RR];
+            unsigned empt = 0u, tz = 0u;
+            if (lane < C) {
 #pragma unroll
-                for (int r = RR - 1; r >= 0; --r) {
-                    const int below = __popc(empt >> (r + 1));     // empties underneath: the cell falls that far
-                    if (!((empt >> r) & 1u) && below) {
-                        col[(r + below) * C + lane] = (int8_t)x[r];
-                        typ[(r + below) * C + lane] = (int8_t)t[r];
+                for (int r = 0; r < RR; ++r) {
+                    x[r] = col[r * C + lane];
+                    t[r] = typ[r * C + lane];
+                    empt |= (unsigned)(x[r] == 0 && t[r] == 0) << r;
+                    tz |= (unsigned)(t[r] == 0) << r;
+                }
+                if (empt) {
+#pragma unroll
+                    for (int r = RR - 1; r >= 0; --r) {
+                        const int below = __popc(empt >> (r + 1));     // empties underneath: the cell falls that far
+                        if (!((empt >> r) & 1u) && below) {
+                            col[(r + below) * C + lane] = (int8_t)x[r];
+                            typ[(r + below) * C + lane] = (int8_t)t[r];
+                        }
                     }
                 }
             }
+            e = __popc(empt);
+            elim_add = radd(__popc(tz));                           // ref :362,374: P - count_nonzero(type)
         }
-        const int e = __popc(empt);
-        elim_add = radd(__popc(tz));                               // ref :362,374: P - count_nonzero(type)
         unsigned m = ballot(e > 0);
         if (!m) return;                                            // ref :238: no rng call when nothing is empty
         if (!p.use_inj) {
@@ -638,6 +693,44 @@ template <int L, int RT = 0, int CT = 0> struct Board {
     __device__ __forceinline__ Bits column_bits(bool all_normal) const {
         Bits b;
         b.E = b.D = b.T = b.S = 0u;
+        if (L == 32 && CT > 0 && CT <= 16 && RT > 1) {
+            // one board per warp: the upper half of the rows on lanes 0..C-1, the lower half on lanes 16..16+C-1, combined
+            // with one xor-shuffle per bitboard -- half the serial row loop
+            constexpr int RH = (RT + 1) / 2;
+            const int c = lane & 15, half = lane >> 4;
+            if (c < C) {
+                const int r0 = half ? RH : 0;
+                int prev = half ? (int)col[(RH - 1) * C + c] : -3;
+                const bool has_right = c + 1 < C;
+#pragma unroll
+                for (int k = 0; k < RH; ++k) {
+                    const int r = r0 + k;
+                    if (r < RT) {
+                        const int i = r * C + c;
+                        const int x = col[i];
+                        const int xr = has_right ? (int)col[i + 1] : -2;
+                        b.E |= (unsigned)(x == xr) << r;
+                        b.D |= (unsigned)(x == prev) << r;
+                        if (!all_normal) {
+                            const int t = typ[i];
+                            b.T |= (unsigned)(t > 0) << r;
+                            b.S |= (unsigned)not01(t) << r;
+                        }
+                        prev = x;
+                    }
+                }
+            }
+            TMG_SITE_HERE
+            b.E |= __shfl_xor_sync(0xffffffffu, b.E, 16);
+            b.D |= __shfl_xor_sync(0xffffffffu, b.D, 16);
+            if (!all_normal) {
+                b.T |= __shfl_xor_sync(0xffffffffu, b.T, 16);
+                b.S |= __shfl_xor_sync(0xffffffffu, b.S, 16);
+            }
+            if (lane >= C) { b.E = b.D = b.T = b.S = 0u; }
+            else if (all_normal) b.T = rows_mask();
+            return b;
+        }
         if (lane < C) {
             int prev = -3;
             const bool has_right = lane + 1 < C;
@@ -1150,9 +1243,11 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             if (ballot((mine && ((b.S >> rs) & 1u)) || len > 4)) return 0;
             const int laser = sp_h ? 3 : (sp_v ? 2 : 0);                      // ref :297-302
             const unsigned create = laser ? (long4 << 1) : 0u;               // second cell of each 4-line
+            if (DEFER_GAPS) { fg_len = 0; fg_valid = true; }
             if (mine) {
                 const int i = rs * C + lane;
                 if ((create >> lane) & 1u) typ[i] = (int8_t)laser;           // keeps the line's colour (ref :596-597)
+                else if (DEFER_GAPS) { fg_top = rs; fg_len = 1; }
                 else { col[i] = 0; typ[i] = 0; }
             }
             n_new += __popc(create);
@@ -1164,7 +1259,13 @@ template <int L, int RT = 0, int CT = 0> struct Board {
             // a cell of the line with an equal horizontal neighbour could start a phase-2 segment (ref :198-214)
             if (ballot((vrows & (b.S | b.E | El)) != 0u || len > 4)) return 0;
             const bool make = sc.has_v && len == 4 && sp_v;                   // vertical 4-line -> vertical laser or normal
-            if (sc.has_v) {
+            if (DEFER_GAPS) {
+                // the laser is created on the second cell (ref :453-456) and falls to the anchor row: write it there
+                fg_valid = true;
+                fg_top = sc.vtop;
+                fg_len = sc.has_v ? (make ? len - 1 : len) : 0;
+                if (make) typ[rs * C + lane] = 2;
+            } else if (sc.has_v) {
                 for (int r = sc.vtop; r <= rs; ++r) {
                     const int i = r * C + lane;
                     if (make && r == sc.vtop + 1) typ[i] = 2;
@@ -1730,6 +1831,9 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
         p.new_specials[env] = 0;
         p.activated[env] = 0;
         p.shuffled[env] = 0;
+        if (p.h_reward) p.h_reward[env] = 0;                 // host mirror: coalesced stores over PCIe
+        if (p.h_terminated) p.h_terminated[env] = (uint8_t)terminated;
+        if (p.h_moves_left && !fault) p.h_moves_left[env] = p.num_moves - timer;
         // The next board is a pure function of (seed, env, episode): take it from the pool k_pregen filled ahead of
         // time when it is there, generate it inside the step otherwise (same result either way).
         bool from_pool = false;
@@ -1816,20 +1920,20 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
     }
     if (from_pool) {                       // board and mask of the new episode come straight from the pool
         b.sync();
-        copy_bytes<L>(p.board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, 2 * p.P, p.board_vecw, lane);
-        if (want_mask) copy_bytes<L>(p.mask + (size_t)env * p.A, p.pool_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
+        b.copy_board(p.board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, p.board_vecw);
+        if (want_mask) b.copy_mask(p.mask + (size_t)env * p.A, p.pool_mask + (size_t)env * p.A);
         b.status |= p.pool_status[env];
         if (eff) b.store_cursors();
-        if (p.h_board) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, 2 * p.P, p.board_vecw, lane);
+        if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, p.board_vecw);
         if (want_mask && (p.h_mask || p.h_mask_bits)) {
-            copy_bytes<L>(b.s.mask, p.pool_mask + (size_t)env * p.A, p.A, p.mask_vecw, lane);
+            b.copy_mask(b.s.mask, p.pool_mask + (size_t)env * p.A);
             b.sync();
             b.mirror_mask(false);
         }
     } else {
         if (dirty) {
             b.store_board(); b.store_cursors();
-            if (p.h_board) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, lane);
+            if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, b.s.board, p.board_vecw);
         }
         if (want_mask) {
             if (zero_mask) { b.store_zero_mask(); b.mirror_mask(true); }
@@ -1844,6 +1948,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
     if (lane == 0) {
         if (regenerate) p.episode[env] = next_ep;
         if (eff) {                         // k_gate wrote the outputs of a step that changes nothing
+            if (p.h_reward) p.h_reward[env] = reward;
             p.reward[env] = reward;
             p.is_comb[env] = (uint8_t)is_comb;
             p.new_specials[env] = n_new;
@@ -1991,7 +2096,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             if (terminal) b.store_zero_mask();
             else if (touched) { b.mask_to_smem(effv, effh); b.store_mask(); }
         }
-        if (p.h_board && touched) copy_bytes<L>(p.h_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, lane);
+        if (p.h_board && touched) b.copy_board(p.h_board + (size_t)env * 2 * p.P, b.s.board, p.board_vecw);
         if (want_mask && p.T > 0 && (terminal || touched)) b.mirror_mask(terminal);
         merge_status(b, p);
         if (touched) {
@@ -2003,6 +2108,11 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             if (regenerated && p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = env;   // next board -> pool
         }
         write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled, timer >= 0);
+        if (lane == 0) {
+            if (p.h_reward) p.h_reward[env] = reward;
+            if (p.h_terminated) p.h_terminated[env] = (uint8_t)terminated;
+            if (p.h_moves_left && timer >= 0) p.h_moves_left[env] = p.num_moves - timer;
+        }
         b.sync();
     }
     if (lane == 0) commit_launch(p, gridDim.x * (uint32_t)Cfg<L>::GPB, false);
@@ -2172,11 +2282,11 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         b.end_generate();
         b.sync();
         const int env = b.env;
-        copy_bytes<L>(p.pool_board + (size_t)env * 2 * p.P, b.s.board, 2 * p.P, p.board_vecw, gc.lane);
+        b.copy_board(p.pool_board + (size_t)env * 2 * p.P, b.s.board, p.board_vecw);
         if (!(p.flags & FLAG_NO_MASK)) {
             b.mask_to_smem(effv, effh);
             b.sync();
-            copy_bytes<L>(p.pool_mask + (size_t)env * p.A, b.s.mask, p.A, p.mask_vecw, gc.lane);
+            b.copy_mask(p.pool_mask + (size_t)env * p.A, b.s.mask);
         }
         const unsigned st = b.ror(b.status);
         if (gc.lane == 0) p.pool_status[env] = st;

@@ -382,9 +382,10 @@ class HostStepper:
 
     def __init__(self, env: TileMatchVecEnv, outputs=("board", "reward", "terminated", "mask", "num_moves_left"),
                  mirror: bool = False):
-        """mirror=True binds board / mask / mask_bits as the host mirror (tmg_host_bind): the step kernel then writes
-        the entries it changes straight into these pinned arrays over PCIe instead of copying every array in full
-        after every step; the arrays hold the complete current state after each call either way."""
+        """mirror=True binds the pinned arrays as the host mirror (tmg_host_bind): the step kernels read the actions in
+        place and write board / mask entries of the envs they change, and reward / terminated / num_moves_left of
+        every env, straight into these arrays over PCIe instead of copying every array in full after every step; the
+        arrays hold the complete current state after each call either way."""
         self.env = env
         self.mirror = mirror
         N, R, Cc, A = env.num_envs, env.num_rows, env.num_cols, env.num_actions
@@ -404,17 +405,19 @@ class HostStepper:
         self.h2d_bytes = self.host["actions"].numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for n, t in self.host.items() if n != "actions")
         if mirror:
-            ptr = lambda n: C.c_void_p(self.host[n].data_ptr()) if n in self.host else None  # noqa: E731
-            nat.check(env._lib.tmg_host_bind(env._h, ptr("board"), ptr("mask"), ptr("mask_bits"), env._stream()), "tmg_host_bind")
+            nat.check(env._lib.tmg_host_bind(env._h, C.byref(self.io), env._stream()), "tmg_host_bind")
             self._mirrored = [n for n in ("board", "mask", "mask_bits") if n in self.host]
-            # per step: the scalar arrays in full + one entry of every mirrored array per env that changed
+            scalars = [n for n in ("reward", "terminated", "num_moves_left") if n in self.host]
+            # per step over PCIe: the mirrored scalars of every env + one entry of every mirrored array per env that
+            # changed + whatever else is copied in full
             self.d2h_bytes_fixed = sum(t.numel() * t.element_size() for n, t in self.host.items()
                                        if n != "actions" and n not in self._mirrored)
             self.d2h_bytes_per_changed_env = sum(self.host[n][0].numel() * self.host[n].element_size() for n in self._mirrored)
+            self.d2h_bytes_per_changed_env += 4 if "reward" in scalars else 0
 
     def close(self):
         if self.mirror:
-            nat.check(self.env._lib.tmg_host_bind(self.env._h, None, None, None, self.env._stream()), "tmg_host_bind")
+            nat.check(self.env._lib.tmg_host_bind(self.env._h, None, self.env._stream()), "tmg_host_bind")
             self.mirror = False
 
     def effective_actions(self, i: int):
