@@ -39,9 +39,9 @@ P = ROWS * COLS
 A = 2 * P - ROWS - COLS
 # algorithmic bytes per env-step = 4P + 48 + A = 628 B for 10x10 (int8 planes in+out, scalars, mask)
 BYTES_PER_STEP = 4 * P + 48 + A
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch (ncu --set full, profiles/r01b_k_work_ncu.txt):
-# 5.78 MB read + 0.20 MB written (no-op steps never load their board; writes stay in the 126 MB L2 within a launch)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 5.98e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch (ncu --set full, profiles/r01c_k_work_ncu.txt):
+# 5.84 MB read + 0.22 MB written (no-op steps never load their board; writes stay in the 126 MB L2 within a launch)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 6.06e6
 METRIC = "env-steps/sec (full cascade, bit-exact)"
 UNIT = "env-steps/s"
 
@@ -311,7 +311,7 @@ def main():
             # k_gate + k_work per step, plus one k_pregen per step on a side stream
             "gpu_launches": 3 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "tmg::k_gate + tmg::k_work<16,10,10> (one tmg_step)",
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peak_src, "kernel": "tmg::k_gate + tmg::k_work<32,10,10> (one tmg_step)",
                          "bytes_per_env_step": BYTES_PER_STEP, "envs_per_launch": n_local,
                          "note": "integer/divergence-bound kernel: the HBM fraction is low by construction, see DESIGN.md"},
             "rollout": {"value": n_global * T * n_win / (rollout_ms * 1e-3), "unit": UNIT, "steps_per_launch": T, "launches": n_win,
