@@ -333,6 +333,12 @@ __device__ __noinline__ void shuffle_serial(int8_t* col, int8_t* typ, int P, uin
     }
 }
 
+// packed rows of a fresh (all-normal) board: one word per row, BITS bits per cell, value = colour - 1
+template <int BITS> __device__ __forceinline__ uint32_t packed_eq(uint32_t t) {   // cells of t that are all-zero -> their low bit
+    if (BITS == 2) return ~(t | (t >> 1)) & 0x55555555u;
+    return ~(t | (t >> 1) | (t >> 2)) & 0x09249249u;
+}
+
 // ======================================================================================================
 // One board owned by a group of L lanes
 // ======================================================================================================
@@ -1582,6 +1588,81 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         return true;
     }
 
+    // generate_board's line removal (ref :95-101, :120-131) on PACKED ROWS, one board per warp: lane r holds row r of the
+    // fresh board as one word of BITS-bit cells (a fresh board is colours only).  The line scan is then a handful of
+    // xor / shift / and on the lane's own word plus two shuffles for the rows above, instead of a pass over the byte
+    // planes, and a redraw assembles each row from the Philox words in shared memory.  Same draws, same order, same
+    // result as begin_generate + the redraw loop of playability(); leaves the line-free board as bytes in shared
+    // memory with the reset-stream cursor and the iteration count where that loop would have left them.
+    static constexpr bool PACKED_GEN = L == 32 && RT > 0 && RT <= 32 && RT * CT + 3 <= 4 * L;
+    template <int BITS> __device__ __forceinline__ void generate_packed(uint32_t ep, int& iters, bool& capped) {
+        constexpr int RR = RT > 0 ? RT : 1, CC = CT > 0 ? CT : 1;
+        constexpr uint32_t cells = (BITS == 2) ? 0x55555555u : 0x09249249u;
+        constexpr uint32_t cmask = (CC * BITS >= 32) ? cells : (cells & ((1u << ((CC * BITS) & 31)) - 1u));   // low bit of cells 0..C-1
+        constexpr uint32_t hmask = cmask & ((1u << (((CC - 1) * BITS) & 31)) - 1u);                          // cells 0..C-2
+        episode = ep;
+        in_reset = true;
+        rsc = 0ull;
+        uint32_t cur = 0u, row = 0u;       // reset-stream cursor (fits 32 bits: max_iters * P draws), this lane's row
+        int n_rows = RR, from = RR - 1;    // ref :96-97: the initial fill draws every row
+        iters = 0; capped = false;
+#pragma unroll 1
+        for (;;) {
+            // cells [0, n_rows * C) in row-major order <- the next draws (ref :97 / :129): cell i takes word cur + i
+            const int off = (int)(cur & 3u);
+            const int nb = (off + n_rows * CC + 3) >> 2;                       // Philox blocks of this redraw, <= L
+            sync();
+            if (lane < nb) {
+                uint32_t w[4];
+                philox4x32_10((cur >> 2) + (uint32_t)lane, ep, gid, 3u, p.key0, p.key1, w);
+                *reinterpret_cast<uint4*>(&s.wbuf[4 * lane]) = *reinterpret_cast<uint4*>(w);
+            }
+            sync();
+            if (lane < n_rows) {
+                const uint32_t* wp = &s.wbuf[off + lane * CC];
+                uint32_t acc = 0u;
+#pragma unroll
+                for (int c = 0; c < CC; ++c) acc |= __umulhi(wp[c], (uint32_t)K) << (c * BITS);
+                row = acc;
+            }
+            cur += (uint32_t)(n_rows * CC);
+            // line scan (ref :149-196 with every tile normal): H = left ends of horizontal triples in this lane's row,
+            // V = bottoms of vertical triples ending in it
+            const uint32_t up1 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)row, 1), up2 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)row, 2);
+            const uint32_t e = packed_eq<BITS>(row ^ (row >> BITS)) & hmask;
+            const uint32_t H = e & (e >> BITS);
+            const uint32_t V = lane >= 2 ? (packed_eq<BITS>(row ^ up1) & packed_eq<BITS>(up1 ^ up2) & cmask) : 0u;
+            const unsigned has = ballot(lane <= from && lane < RR && (H | V) != 0u);
+            if (!has) break;                                                   // line-free
+            if (iters >= p.max_iters) { status |= ST_RESET_CAP; capped = true; break; }
+            ++iters;
+            ++prof_iters;
+            const int rs = 31 - __clz((int)has);                               // bottom-most row with an anchored line (ref :158-160)
+            // first line of the list (ref :127-128): lowest column, vertical before horizontal at the same column
+            const int cvl = V ? (__ffs((int)V) - 1) : 1024, chl = H ? (__ffs((int)H) - 1) : 1024;
+            const int cv = shfl(cvl, rs), ch = shfl(chl, rs);
+            int top = rs;
+            if (cv <= ch) {
+                // vertical: extend upwards while the cell above has the colour (ref :168-172); D bit r: rows r and r-1 agree at cv
+                const unsigned D = ballot(lane >= 1 && lane < RR && (((row ^ up1) >> cv) & ((1u << BITS) - 1u)) == 0u);
+                top = rs - __clz((int)~(D << (31 - rs)));
+            }
+            const int ri = min(RR - 1, top + 1);
+            n_rows = ri + 1;
+            from = min(RR - 1, max(rs, ri + 2));                               // rows below were line-free and their 3-windows are unchanged
+        }
+        rdc = (uint64_t)cur;
+        // the board as bytes, for possible_move / shuffle, the mask and the pool entry
+        sync();
+        if (lane < RR) {
+#pragma unroll
+            for (int c = 0; c < CC; ++c) col[lane * CC + c] = (int8_t)(1 + (int)((row >> (c * BITS)) & ((1u << BITS) - 1u)));
+        }
+#pragma unroll 1
+        for (int i = lane; i < RR * CC; i += L) typ[i] = 1;
+        sync();
+    }
+
     // move (ref :330-378) after the effectiveness gate, in the pieces the kernels schedule:
     // move_begin = counters, swap and the combination match (ref :343-361), returns is_combination_match -- its
     // gravity + refill (ref :362-364) is left to the first cascade_trip; cascade_trip = one trip of the cascade
@@ -2267,6 +2348,11 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
                             }
                         }
                         b.sync();
+                    } else if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
+                        // fixed small shapes: the whole line removal on packed rows, then straight to the finish
+                        if (p.K <= 4) b.template generate_packed<2>((uint32_t)ep, iters, capped);
+                        else b.template generate_packed<3>((uint32_t)ep, iters, capped);
+                        staged = true;
                     } else {
                         b.begin_generate((uint32_t)ep);        // ref :96-97
                     }
