@@ -121,11 +121,9 @@ template <int L> static void e_step() {
     else k_work<L, 0, 0>(g_params);
 }
 static void e_gate() { k_gate(g_params); }
-static void e_gen2() { k_gen_lines<2>(g_params); }
-static void e_gen3() { k_gen_lines<3>(g_params); }
 // one thread per env, whole warps (k_gate)
-static void launch_threads(void (*fn)(), int n) {
-    const int grid = (n + 127) / 128;
+static void launch_threads(void (*fn)(), int n, int per_thread = 1) {
+    const int grid = (n + 128 * per_thread - 1) / (128 * per_thread);
     emu::block_dim = emu::Dim{128u, 1, 1};
     emu::grid_dim = emu::Dim{(unsigned)grid, 1, 1};
     for (int b = 0; b < grid; ++b) {
@@ -203,10 +201,10 @@ void* emu_create(const emu_config* c) {
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
     size_t cap = 1;
     while (cap < N) cap <<= 1;
-    size_t o[23] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
+    size_t o[22] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
                     take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4), take(N * 4), take(N * 4),
                     take(N * 2 * p.P), take(N * p.A), take(N * 4), take(CTL_WORDS * 4), take(N * 8), take(cap * 4),
-                    take(N * STAGE_WORDS * 4), take(N)};
+                    take(N)};
     e->mem.assign(off + 256, 0);
     char* b = e->mem.data();
     b += (256 - ((uintptr_t)b & 255)) & 255;
@@ -220,11 +218,7 @@ void* emu_create(const emu_config* c) {
     p.ctl = (uint32_t*)(b + o[18]); p.wl_items = (uint2*)(b + o[19]); p.req_mask = (uint32_t)(cap - 1);
     const bool pregen = !p.use_inj && !(p.flags & 2u) && p.autoreset != 0;
     p.req_ring = pregen ? (int32_t*)(b + o[20]) : nullptr;
-    p.pool_stage = (uint32_t*)(b + o[21]); p.n_special = (uint8_t*)(b + o[22]);
-    if (pregen && p.R <= STAGE_ROWS && getenv("TMG_B200_GEN_LINES")) {
-        if (p.K <= 4 && 2 * p.C <= 32) p.gen_bits = 2;
-        else if (p.K <= 8 && 3 * p.C <= 32) p.gen_bits = 3;
-    }
+    p.n_special = (uint8_t*)(b + o[21]);
     for (size_t i = 0; i < N; ++i) { p.timer[i] = -1; p.episode[i] = -1; p.pool_episode[i] = (int32_t)0x80808080; }
     return e;
 }
@@ -258,18 +252,16 @@ void emu_reset(void* h, const uint8_t* reset_mask, const int8_t* init_boards) {
     DISPATCH(e_reset)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
         g_params = e->p; g_params.pool_tag = e->tag++;
-        if (e->p.gen_bits) launch_threads(e->p.gen_bits == 2 ? e_gen2 : e_gen3, e->p.N);
         DISPATCH(e_pregen)
     }
 }
 void emu_step(void* h, const int32_t* actions) {
     EmuEnv* e = (EmuEnv*)h;
     g_params = e->p; g_params.actions = actions; g_params.pool_tag = e->tag; g_params.seq = e->seq++ & 1;
-    launch_threads(e_gate, e->p.N);
+    launch_threads(e_gate, e->p.N, GATE_EPT);
     DISPATCH(e_step)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
         g_params = e->p; g_params.pool_tag = e->tag++;
-        if (e->p.gen_bits) launch_threads(e->p.gen_bits == 2 ? e_gen2 : e_gen3, e->p.N);
         DISPATCH(e_pregen)
     }
 }
@@ -280,7 +272,6 @@ void emu_step_many(void* h, const int32_t* actions, int T, int32_t* rewards, uin
     DISPATCH(e_rollout)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
         g_params = e->p; g_params.pool_tag = e->tag++;
-        if (e->p.gen_bits) launch_threads(e->p.gen_bits == 2 ? e_gen2 : e_gen3, e->p.N);
         DISPATCH(e_pregen)
     }
 }

@@ -45,6 +45,23 @@ def test_emulated_batch_vs_oracle(cfg):
             assert np.array_equal(getattr(e, f), getattr(o, f)), (t, f)
 
 
+@pytest.mark.parametrize("R,C,K,cap", [(10, 10, 4, 6), (9, 9, 6, 2), (6, 7, 3, 4)])
+def test_emulated_reset_cap_is_flagged_identically(R, C, K, cap):
+    """generate_board stopped by max_reset_iters (TMG_ST_RESET_CAP): same boards, cursors and status bits as the
+    oracle, on the packed-row generator (fixed shapes) and the byte-plane one."""
+    N, moves = 32, 3
+    e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=6, autoreset="same_step", max_reset_iters=cap)
+    o = orc.OracleVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=6, autoreset="same_step", max_reset_iters=cap, num_threads=4)
+    e.reset(); o.reset()
+    assert (o.status & 8).any()                      # the cap is actually hit
+    rng = np.random.default_rng(2)
+    for t in range(2 * moves + 1):
+        for f in ("board", "mask", "status", "draw_cursor", "shuffle_cursor", "episode"):
+            assert np.array_equal(getattr(e, f), getattr(o, f)), (t, f)
+        a = rng.integers(0, o.A, N).astype(np.int32)
+        e.step(a); o.step(a)
+
+
 @pytest.mark.parametrize("R,C,K,moves,autoreset,T", [
     (10, 10, 4, 5, "same_step", 13), (9, 9, 6, 4, "next_step", 11), (4, 5, 3, 3, "same_step", 10), (6, 7, 4, 6, "disabled", 9),
     (10, 10, 4, 30, "same_step", 6)])
@@ -75,23 +92,6 @@ def test_emulated_step_many_equals_single_steps(R, C, K, moves, autoreset, T):
         e.step(acts[0]); o.step(acts[0])      # single steps and rollouts interleave
         for f in fields:
             assert np.array_equal(getattr(e, f), getattr(o, f)), (window, "after single step", f)
-
-
-@pytest.mark.parametrize("R,C,K", [(10, 10, 4), (9, 9, 6), (3, 5, 3), (6, 8, 3)])
-def test_emulated_thread_per_board_generator_gives_the_same_boards(R, C, K, monkeypatch):
-    """k_gen_lines (opt-in first stage of the pool refill, one thread per board on packed rows) must produce exactly
-    the boards of the group kernel: compare whole trajectories with same-step autoreset against the oracle."""
-    monkeypatch.setenv("TMG_B200_GEN_LINES", "1")
-    N, moves = 20, 3
-    e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=9, autoreset="same_step", env_id_offset=3)
-    o = orc.OracleVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=9, autoreset="same_step", env_id_offset=3, num_threads=4)
-    e.reset(); o.reset()
-    rng = np.random.default_rng(1)
-    for t in range(4 * moves):
-        a = rng.integers(0, o.A, N).astype(np.int32)
-        e.step(a); o.step(a)
-        assert np.array_equal(e.board, o.board) and np.array_equal(e.mask, o.mask), t
-        assert np.array_equal(e.shuffle_cursor, o.shuffle_cursor) and np.array_equal(e.status, o.status), t
 
 
 @pytest.mark.parametrize("R,C,K,moves,autoreset", [(10, 10, 4, 6, "same_step"), (5, 7, 3, 4, "disabled"), (9, 9, 6, 5, "next_step")])

@@ -30,7 +30,6 @@ struct tmg_env {
     long long step_count;     // number of tmg_step calls so far (parity selects the work-list counters)
     int persistent_blocks;    // resident-block slots of the device for k_work / k_pregen (persistent groups)
     int pregen_grid_cap;      // diagnostics: cap on the blocks of a k_pregen launch
-    int gen_blocks;           // blocks of a k_gen_lines launch (persistent threads)
     bool pregen;              // pool in use (philox refill, not disabled by flag)
     // host mirror (tmg_host_bind): the caller's page-locked arrays; p.h_* are their device-visible aliases
     int8_t* hm_board;
@@ -112,14 +111,6 @@ static int launch_pregen(tmg_env* e, cudaStream_t st) {
     if (cudaStreamWaitEvent(side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
     Params p = e->p;
     p.pool_tag = (int)(tag & 0x7fffffff);
-    if (p.gen_bits) {
-        int grid = (p.N + 127) / 128;
-        if (grid > e->gen_blocks) grid = e->gen_blocks;
-        const size_t smem = (size_t)p.R * 128 * 4;
-        if (p.gen_bits == 2) k_gen_lines<2><<<grid, 128, smem, side>>>(p);
-        else k_gen_lines<3><<<grid, 128, smem, side>>>(p);
-        if (last_error() != TMG_OK) return TMG_ERR_CUDA;
-    }
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
@@ -237,7 +228,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
                  o_pool_status = take((size_t)N * 4), o_mask_bits = take((size_t)N * ((p.A + 7) / 8)),
                  o_ctl = take((size_t)CTL_WORDS * 4), o_items = take((size_t)N * sizeof(uint2)),
-                 o_stage = take((size_t)N * STAGE_WORDS * 4), o_nsp = take((size_t)N);
+                 o_nsp = take((size_t)N);
     size_t req_cap = 1;
     while (req_cap < (size_t)N) req_cap <<= 1;
     const size_t o_ring = take(req_cap * 4);
@@ -267,7 +258,6 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.ctl = reinterpret_cast<uint32_t*>(b + o_ctl);
     p.wl_items = reinterpret_cast<uint2*>(b + o_items);
     p.req_mask = (uint32_t)(req_cap - 1);
-    p.pool_stage = reinterpret_cast<uint32_t*>(b + o_stage);
     p.n_special = reinterpret_cast<uint8_t*>(b + o_nsp);
     e->mask_bits_dev = reinterpret_cast<uint8_t*>(b + o_mask_bits);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
@@ -276,20 +266,6 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr; e->hm_terminated = nullptr;
     e->hm_reward = nullptr; e->hm_moves_left = nullptr; e->hm_bound = false;
     p.req_ring = e->pregen ? reinterpret_cast<int32_t*>(b + o_ring) : nullptr;
-    // Thread-per-board first stage of the pool refill (k_gen_lines): boards whose rows fit one 32-bit word of 2- or 3-bit
-    // cells.  EXPERIMENT, opt-in (TMG_B200_GEN_LINES=1): bit-exact, but measured no faster than the group kernel at 65 536
-    // envs (199 M vs 196 M env-steps/s) and far slower when few boards are requested per launch -- with one board per
-    // thread a warp runs as long as its slowest board and each redraw is up to 25 dependent Philox blocks.
-    p.gen_bits = 0;
-    if (e->pregen && R <= STAGE_ROWS && getenv("TMG_B200_GEN_LINES")) {
-        if (K <= 4 && 2 * C <= 32) p.gen_bits = 2;
-        else if (K <= 8 && 3 * C <= 32) p.gen_bits = 3;
-    }
-    e->gen_blocks = prop.multiProcessorCount * 4;
-    {
-        const char* gb = getenv("TMG_B200_GEN_BLOCKS_PER_SM");   // tuning knob
-        if (gb && atoi(gb) > 0) e->gen_blocks = prop.multiProcessorCount * atoi(gb);
-    }
     e->persistent_blocks = prop.multiProcessorCount * TMG_STEP_MIN_BLOCKS;
     {
         const char* ppsm = getenv("TMG_B200_BLOCKS_PER_SM");   // tuning knob: persistent blocks per SM
@@ -434,7 +410,7 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
         const long long W = p.num_moves < 24 ? p.num_moves : 24;   // < RING - SIDE so the event slots are still live
         if (!wait_pregen(e, st, e->pregen_count - W)) return TMG_ERR_CUDA;
     }
-    k_gate<<<(p.N + 127) / 128, 128, 0, st>>>(p);
+    k_gate<<<(p.N + 128 * GATE_EPT - 1) / (128 * GATE_EPT), 128, 0, st>>>(p);
     if (last_error() != TMG_OK) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;

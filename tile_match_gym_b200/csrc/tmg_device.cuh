@@ -92,8 +92,6 @@ struct Params {
     uint8_t* pool_mask;      // [N][A]       its legal-move mask
     int32_t* pool_episode;   // [N]          which episode the pool entry belongs to (-1 = none)
     uint32_t* pool_status;   // [N]          status bits raised while generating it (merged when it is consumed)
-    uint32_t* pool_stage;    // [N][STAGE_WORDS] line-free board of k_gen_lines awaiting k_pregen: rows, draw cursor, iterations, flags
-    int gen_bits;            // bits per cell of the thread-per-board generator (2: K <= 4, 3: K <= 8), 0 = not applicable
     int pool_tag;            // number of the k_pregen launch that serves the requests of this launch (k_gate / k_reset)
     // scheduling state (device): see Ctl below
     uint32_t* ctl;           // control words
@@ -137,14 +135,12 @@ enum {
     CTL_REQ_PREV = 6,        // CTL_REQ_TAIL at the end of the previous requesting launch
     CTL_PG_RANGE = 8,        // [PG_RING][2] request range served by k_pregen launch `tag`, at tag % PG_RING
     CTL_PG_HEAD = CTL_PG_RANGE + 2 * PG_RING,   // [PG_RING] pop cursor of that launch
-    CTL_PG_HEAD2 = CTL_PG_HEAD + PG_RING,       // [PG_RING] pop cursor of its first stage (k_gen_lines)
-    CTL_RO_HEAD = CTL_PG_HEAD2 + PG_RING,       // pop cursor of k_rollout over the envs
+    CTL_RO_HEAD = CTL_PG_HEAD + PG_RING,        // pop cursor of k_rollout over the envs
     CTL_WL_COUNT_LO = CTL_RO_HEAD + 1,          // [2] normal-priority items (CTL_WL_COUNT counts the high-priority ones)
     CTL_WORDS = CTL_WL_COUNT_LO + 2
 };
 enum { PRI_SPECIALS = 4 };   // a move on a board with this many special tiles is scheduled first: 23 % of the effective
                              // moves, 80 % of the longest 1 % of the cascades (10x10, 4 colours, measured on the CPU restatement)
-enum { STAGE_ROWS = 16, STAGE_RDC = 16, STAGE_ITERS = 17, STAGE_FLAGS = 18, STAGE_WORDS = 20 };
 enum : uint32_t { IT_ACTION = 0xfffu, IT_EFF = 1u << 12, IT_REGEN = 1u << 13, IT_ZERO_MASK = 1u << 14, IT_FROM_POOL = 1u << 15 };
 
 template <int L> struct Cfg {
@@ -1805,7 +1801,6 @@ __device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers,
     p.ctl[CTL_PG_RANGE + 2 * slot] = prev;
     p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
     p.ctl[CTL_PG_HEAD + slot] = 0u;
-    p.ctl[CTL_PG_HEAD2 + slot] = 0u;
     p.ctl[CTL_REQ_PREV] = tail;
     p.ctl[CTL_RO_HEAD] = 0u;
     if (is_step) {
@@ -1841,8 +1836,17 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         } else {
             const int ep = p.episode[gc.env] + 1;    // generate_board (ref board.py:95-112)
             b.sync();
-            b.begin_generate((uint32_t)ep);
-            b.playability(false, true, effv, effh);
+            if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
+                int iters = 0;                       // line removal on packed rows, as in k_pregen
+                bool capped = false;
+                if (p.K <= 4) b.template generate_packed<2>((uint32_t)ep, iters, capped);
+                else b.template generate_packed<3>((uint32_t)ep, iters, capped);
+                if (capped) b.mask_bits(effv, effh);
+                else b.playability(true, true, effv, effh, iters);
+            } else {
+                b.begin_generate((uint32_t)ep);
+                b.playability(false, true, effv, effh);
+            }
             b.end_generate();
             if (gc.lane == 0) {
                 p.episode[gc.env] = ep;
@@ -1866,13 +1870,18 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 // effectiveness gate (ref board.py:352: the maintained mask IS is_move_effective of the current board, so a no-op
 // step reads one byte and never touches its board) and the outputs of a step that changes nothing.  Envs that need
 // board work -- an effective move, a new board, a zeroed mask -- go to the work list.
+enum { GATE_EPT = 4 };   // envs per thread of k_gate: four independent chains of dependent loads per thread, a quarter of the atomics
 __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) {
-    const int env = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const int wl = (int)threadIdx.x & 31;
+    const int env0 = ((int)blockIdx.x * 4 + ((int)threadIdx.x >> 5)) * (32 * GATE_EPT) + wl;   // this thread: env0 + 32 k
     const int q = p.seq & 1;
-    bool heavy = false, req = false;
-    uint32_t packed = 0u;
-    if (env < p.N) {
+    bool heavy[GATE_EPT], hi[GATE_EPT], req[GATE_EPT];
+    uint32_t packed[GATE_EPT];
+#pragma unroll
+    for (int k = 0; k < GATE_EPT; ++k) {
+        const int env = env0 + 32 * k;
+        heavy[k] = false; hi[k] = false; req[k] = false; packed[k] = 0u;
+        if (env >= p.N) continue;
         int timer = p.timer[env];
         const int action = p.actions[env];
         bool eff = false, regenerate = false, fault = false;
@@ -1919,30 +1928,42 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
         // time when it is there, generate it inside the step otherwise (same result either way).
         bool from_pool = false;
         if (regenerate) from_pool = !p.use_inj && p.pool_episode[env] == p.episode[env] + 1;
-        heavy = eff || regenerate || zero_mask;
-        req = regenerate && p.req_ring != nullptr;
-        packed = ((uint32_t)action & IT_ACTION) | (eff ? IT_EFF : 0u) | (regenerate ? IT_REGEN : 0u) |
-                 (zero_mask ? IT_ZERO_MASK : 0u) | (from_pool ? IT_FROM_POOL : 0u);
+        heavy[k] = eff || regenerate || zero_mask;
+        hi[k] = eff && p.n_special[env] >= PRI_SPECIALS;
+        req[k] = regenerate && p.req_ring != nullptr;
+        packed[k] = ((uint32_t)action & IT_ACTION) | (eff ? IT_EFF : 0u) | (regenerate ? IT_REGEN : 0u) |
+                    (zero_mask ? IT_ZERO_MASK : 0u) | (from_pool ? IT_FROM_POOL : 0u);
     }
-    const bool hi = heavy && (packed & IT_EFF) && p.n_special[env] >= PRI_SPECIALS;
+    // one append per list and warp: positions by ballot
+    unsigned hm[GATE_EPT], lm[GATE_EPT], rm[GATE_EPT];
+    uint32_t nh = 0u, nl = 0u, nr = 0u;
     TMG_SITE_HERE
-    const unsigned hm = __ballot_sync(0xffffffffu, hi), lm = __ballot_sync(0xffffffffu, heavy && !hi),
-                   rm = __ballot_sync(0xffffffffu, req);
+#pragma unroll
+    for (int k = 0; k < GATE_EPT; ++k) {
+        hm[k] = __ballot_sync(0xffffffffu, hi[k]);
+        lm[k] = __ballot_sync(0xffffffffu, heavy[k] && !hi[k]);
+        rm[k] = __ballot_sync(0xffffffffu, req[k]);
+        nh += (uint32_t)__popc(hm[k]); nl += (uint32_t)__popc(lm[k]); nr += (uint32_t)__popc(rm[k]);
+    }
     uint32_t hbase = 0u, lbase = 0u, rbase = 0u;
     if (wl == 0) {
-        if (hm) hbase = atomicAdd(&p.ctl[CTL_WL_COUNT + q], (uint32_t)__popc(hm));
-        if (lm) lbase = atomicAdd(&p.ctl[CTL_WL_COUNT_LO + q], (uint32_t)__popc(lm));
-        if (rm) rbase = atomicAdd(&p.ctl[CTL_REQ_TAIL], (uint32_t)__popc(rm));
+        if (nh) hbase = atomicAdd(&p.ctl[CTL_WL_COUNT + q], nh);
+        if (nl) lbase = atomicAdd(&p.ctl[CTL_WL_COUNT_LO + q], nl);
+        if (nr) rbase = atomicAdd(&p.ctl[CTL_REQ_TAIL], nr);
     }
     hbase = (uint32_t)__shfl_sync(0xffffffffu, (int)hbase, 0);
     lbase = (uint32_t)__shfl_sync(0xffffffffu, (int)lbase, 0);
     rbase = (uint32_t)__shfl_sync(0xffffffffu, (int)rbase, 0);
     const unsigned lt = (1u << wl) - 1u;
-    if (heavy) {
-        uint2 it; it.x = (uint32_t)env; it.y = packed;
-        p.wl_items[hi ? hbase + (uint32_t)__popc(hm & lt) : (uint32_t)p.N - 1u - (lbase + (uint32_t)__popc(lm & lt))] = it;
+#pragma unroll
+    for (int k = 0; k < GATE_EPT; ++k) {
+        if (heavy[k]) {
+            uint2 it; it.x = (uint32_t)(env0 + 32 * k); it.y = packed[k];
+            p.wl_items[hi[k] ? hbase + (uint32_t)__popc(hm[k] & lt) : (uint32_t)p.N - 1u - (lbase + (uint32_t)__popc(lm[k] & lt))] = it;
+        }
+        if (req[k]) p.req_ring[(rbase + (uint32_t)__popc(rm[k] & lt)) & p.req_mask] = env0 + 32 * k;
+        hbase += (uint32_t)__popc(hm[k]); lbase += (uint32_t)__popc(lm[k]); rbase += (uint32_t)__popc(rm[k]);
     }
-    if (req) p.req_ring[(rbase + (uint32_t)__popc(rm & lt)) & p.req_mask] = env;
     __syncwarp(0xffffffffu);
     if (wl == 0) commit_launch(p, gridDim.x * (blockDim.x >> 5), true);
 }
@@ -2199,112 +2220,9 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
     if (lane == 0) commit_launch(p, gridDim.x * (uint32_t)Cfg<L>::GPB, false);
 }
 
-// =====================================================================================================
-// generate_board (ref board.py:95-112), first stage: ONE THREAD per board.
-// A fresh board is all normal tiles, so it is colours only: a row is one 32-bit word of BITS-bit cells (value =
-// colour - 1), the R rows of a thread sit in its private column of shared memory.  remove_colour_lines (ref :120-131)
-// then needs no cross-lane traffic at all: the line scan is a handful of xor / shift / and per row, from the bottom
-// row up to the first row with a line, and the redraw turns Philox blocks straight into row words.  About 86 such
-// iterations per 10x10 / 4-colour board (max > 500), each a dependent chain: one board per thread keeps 32 of them in
-// flight per warp instead of 2, and a thread that finishes its board takes the next request.  Produces the line-free
-// board; possible_move / shuffle (ref :102-109), rare, and the mask are left to k_pregen (second stage).
-// Draws: the episode-indexed reset stream, cell i of a redraw takes word rdc + i -- exactly as Board::draw_cells.
-// =====================================================================================================
-template <int BITS> __device__ __forceinline__ uint32_t gen_eq(uint32_t t) {   // cells of t that are all-zero -> their low bit
-    if (BITS == 2) return ~(t | (t >> 1)) & 0x55555555u;
-    return ~(t | (t >> 1) | (t >> 2)) & 0x09249249u;
-}
-template <int BITS> __global__ void __launch_bounds__(128) k_gen_lines(const __grid_constant__ Params p) {
-    extern __shared__ __align__(16) unsigned char tmg_smem_raw[];
-    uint32_t* rows = reinterpret_cast<uint32_t*>(tmg_smem_raw) + threadIdx.x;   // row r of this thread: rows[r * 128]
-    const int R = p.R, C = p.C;
-    const uint32_t K = (uint32_t)p.K;
-    const int slot = p.pool_tag % PG_RING;
-    const uint32_t start = p.ctl[CTL_PG_RANGE + 2 * slot], n_req = p.ctl[CTL_PG_RANGE + 2 * slot + 1] - start;
-    const uint32_t cells = (BITS == 2) ? 0x55555555u : 0x09249249u;
-    const uint32_t cmask = (C * BITS >= 32) ? cells : (cells & ((1u << (C * BITS)) - 1u));   // low bit of cells 0..C-1
-    const uint32_t hmask = cmask & ((1u << ((C - 1) * BITS)) - 1u);                         // cells 0..C-2
-    int env = -1, iters = 0, from = 0, n_draw = 0;
-    uint32_t ep = 0u, gid = 0u, rdc = 0u;
-#pragma unroll 1
-    for (;;) {
-        if (env < 0) {                                          // take the next request
-            const uint32_t idx = atomicAdd(&p.ctl[CTL_PG_HEAD2 + slot], 1u);
-            if (idx >= n_req) break;
-            env = p.req_ring[(start + idx) & p.req_mask];
-            ep = (uint32_t)(p.episode[env] + 1);
-            if (p.pool_episode[env] == (int)ep) { env = -1; continue; }
-            gid = (uint32_t)(p.env_id_offset + (uint64_t)env);
-            rdc = 0u; iters = 0;
-            n_draw = R * C;                                      // ref :96-97: the initial fill
-            from = R - 1;
-        }
-        {   // cells [0, n_draw) in row-major order <- the next n_draw draws (ref :97 / :129); n_draw is whole rows
-            uint32_t blk = rdc >> 2;
-            int skip = (int)(rdc & 3u), i = 0, r = 0, c = 0;
-            uint32_t acc = 0u;
-#pragma unroll 1
-            while (i < n_draw) {
-                uint32_t w[4];
-                philox4x32_10(blk, ep, gid, 3u, p.key0, p.key1, w);
-                ++blk;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < skip || i >= n_draw) continue;
-                    acc |= __umulhi(w[j], K) << (c * BITS);
-                    ++i;
-                    if (++c == C) { rows[r * 128] = acc; ++r; c = 0; acc = 0u; }
-                }
-                skip = 0;
-            }
-            rdc += (uint32_t)n_draw;
-        }
-        // line scan from row `from` upwards to the bottom-most row with an anchored line (ref :149-196, all tiles normal)
-        int rs = from;
-        uint32_t x0 = rows[rs * 128], x1 = rs >= 1 ? rows[(rs - 1) * 128] : 0u, x2 = rs >= 2 ? rows[(rs - 2) * 128] : 0u;
-        uint32_t H = 0u, V = 0u;
-#pragma unroll 1
-        for (;;) {
-            const uint32_t e = gen_eq<BITS>(x0 ^ (x0 >> BITS)) & hmask;   // cell == right neighbour
-            H = e & (e >> BITS);                                          // left end of a horizontal triple (ref :179-189)
-            V = rs >= 2 ? (gen_eq<BITS>(x0 ^ x1) & gen_eq<BITS>(x1 ^ x2) & cmask) : 0u;   // bottom of a vertical triple (ref :163-173)
-            if ((H | V) || rs == 0) break;
-            --rs;
-            x0 = x1; x1 = x2; x2 = rs >= 2 ? rows[(rs - 2) * 128] : 0u;
-        }
-        bool capped = false;
-        if (H | V) {
-            if (iters < p.max_iters) {                         // remove_colour_lines (ref :120-131)
-                ++iters;
-                const int cv = V ? (__ffs((int)V) - 1) : 1024, ch = H ? (__ffs((int)H) - 1) : 1024;   // bit positions: same order as columns
-                int top = rs;                                  // first line horizontal: l[0][0] is in row rs
-                if (cv <= ch) {                                // vertical lines are listed first at the same column (ref :163,179)
-                    top = rs - 2;
-                    const uint32_t sel = ((1u << BITS) - 1u) << cv;
-#pragma unroll 1
-                    while (top >= 1 && ((rows[(top - 1) * 128] ^ x2) & sel) == 0u) --top;   // x2 = row rs-2: extend upwards (ref :168-172)
-                }
-                const int row = min(R - 1, top + 1);
-                n_draw = (row + 1) * C;
-                from = min(R - 1, max(rs, row + 2));           // rows below were line-free and none of their 3-windows changed
-                continue;
-            }
-            capped = true;
-        }
-        // line-free (or capped): hand the board to the second stage
-        uint32_t* st = p.pool_stage + (size_t)env * STAGE_WORDS;
-#pragma unroll 1
-        for (int r = 0; r < R; ++r) st[r] = rows[r * 128];
-        st[STAGE_RDC] = rdc;
-        st[STAGE_ITERS] = (uint32_t)iters;
-        st[STAGE_FLAGS] = capped ? 1u : 0u;
-        env = -1;
-    }
-}
-
-// Pool refill: generate_board (ref board.py:95-112) of the next board of every env whose request this launch serves
-// (with k_gen_lines enabled, only its second stage: possible_move / shuffle and the mask).  Runs on a side stream,
-// off the step path; touches no env state.
+// Pool refill: generate_board (ref board.py:95-112) of the next board of every env whose request this launch serves.
+// Runs on a side stream, off the step path; touches no env state.  The fixed small shapes remove the lines on packed
+// rows (Board::generate_packed); the others run the byte-plane loop, one scan + redraw iteration per trip.
 // The kernel is issue-bound (ncu: 70 % issue slots busy, instruction-cache hit rate 99.98 %), and a board needs ~86
 // identical scan + redraw iterations, so the groups of a warp are kept CONVERGED: the loop below is one iteration per
 // trip for every group of the warp, with a warp-wide reconvergence point at the top, and a group that finishes its
@@ -2315,7 +2233,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
     const int slot = p.pool_tag % PG_RING;
     const uint32_t start = p.ctl[CTL_PG_RANGE + 2 * slot], n = p.ctl[CTL_PG_RANGE + 2 * slot + 1] - start;
     Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, 0);
-    bool have = false, done = false, capped = false, staged = false;
+    bool have = false, done = false, capped = false, staged = false;   // staged: the line-free board is already in shared memory
     int from = 0, iters = 0, ep = 0;
 #pragma unroll 1
     for (;;) {
@@ -2330,25 +2248,8 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
                     b.rebind(env);
                     b.sync();
                     capped = false; from = b.R - 1; iters = 0; have = true;
-                    staged = p.gen_bits != 0;
-                    if (staged) {              // the line-free board comes from k_gen_lines: expand it to bytes
-                        const uint32_t* st = p.pool_stage + (size_t)env * STAGE_WORDS;
-                        const int BITS = p.gen_bits;
-                        b.episode = (uint32_t)ep;
-                        b.in_reset = true;
-                        b.rdc = (uint64_t)st[STAGE_RDC]; b.rsc = 0ull;
-                        iters = (int)st[STAGE_ITERS];
-                        capped = st[STAGE_FLAGS] & 1u;
-                        if (capped) b.status |= ST_RESET_CAP;
-                        if (gc.lane < b.C) {
-#pragma unroll 1
-                            for (int r = 0; r < b.R; ++r) {
-                                b.col[r * b.C + gc.lane] = (int8_t)(1 + (int)((st[r] >> (gc.lane * BITS)) & ((1u << BITS) - 1u)));
-                                b.typ[r * b.C + gc.lane] = 1;
-                            }
-                        }
-                        b.sync();
-                    } else if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
+                    staged = false;
+                    if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
                         // fixed small shapes: the whole line removal on packed rows, then straight to the finish
                         if (p.K <= 4) b.template generate_packed<2>((uint32_t)ep, iters, capped);
                         else b.template generate_packed<3>((uint32_t)ep, iters, capped);
