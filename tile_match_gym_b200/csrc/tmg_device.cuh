@@ -46,9 +46,7 @@
 #ifndef TMG_FUSED_FALL
 #define TMG_FUSED_FALL 1
 #endif
-#ifndef TMG_PACKED_ROUNDS
-#define TMG_PACKED_ROUNDS 0   // measured slower: 563 -> 510 M steps/s at 262 144 envs
-#endif
+
 
 namespace tmg {
 constexpr int UNROLL_PHILOX = TMG_UNROLL_PHILOX, UNROLL_ROWS = TMG_UNROLL_ROWS;
@@ -1662,145 +1660,6 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         sync();
     }
 
-    // ---------------------------------------------------------------------------------------------------------
-    // Cascade rounds on PACKED ROWS (one board per warp, fixed small shapes, K <= 7): lane r holds row r as two words of
-    // 3-bit cells (colour, type & 7).  A "simple" round -- the lines anchored on the bottom-most line row are all 3 or 4
-    // long, all horizontal or all vertical, made of normal tiles only and without crossing segments: exactly the
-    // rounds fast_round() accepts -- is then a few mask operations: the scan is xor / shift / and on the lane's own
-    // words and the rows above (shuffles), gravity is a masked shuffle from the row 1 / 3 / 4 above, and the refill
-    // ranks follow from the masks alone.  Anything else hands the board back to the byte-plane path, which is always
-    // correct; so every test below may err on the side of "not simple".  Returns true if the cascade ended here (board
-    // stable), false if the byte path must continue; the board is back in shared memory either way.
-    // ---------------------------------------------------------------------------------------------------------
-    static constexpr bool PACKED_ROUNDS = TMG_PACKED_ROUNDS && L == 32 && RT > 0 && RT <= 32 && CT > 0 && 3 * CT <= 32;
-    __device__ __forceinline__ bool packed_cascade(int& elim) {
-        constexpr int RR = RT > 0 ? RT : 1, CC = CT > 0 ? CT : 1, B = 3;
-        constexpr uint32_t cells = 0x09249249u;
-        constexpr uint32_t cmask = (CC * B >= 32) ? cells : (cells & ((1u << ((CC * B) & 31)) - 1u));   // low bit of cells 0..C-1
-        constexpr uint32_t hmask = cmask & ((1u << (((CC - 1) * B) & 31)) - 1u);                       // cells 0..C-2
-        const bool sp_v = specials & SP_VLASER, sp_h = specials & SP_HLASER;
-        // pack this lane's row
-        uint32_t crow = 0u, trow = 0u;
-        bool odd = false;
-        sync();
-        if (lane < RR) {
-#pragma unroll
-            for (int c = 0; c < CC; ++c) {
-                const int x = col[lane * CC + c], t = typ[lane * CC + c];
-                odd |= (x & ~7) != 0;
-                crow |= (uint32_t)(x & 7) << (c * B);
-                trow |= (uint32_t)(t & 7) << (c * B);
-            }
-        }
-        if (ballot(odd)) return false;                                     // colours beyond 3 bits: byte path
-        bool changed = false, stable = false;
-#pragma unroll 1
-        for (;;) {
-            // ---- scan ----
-            const uint32_t cu1 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)crow, 1), cu2 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)crow, 2);
-            const bool in = lane < RR;
-            const uint32_t e = in ? (packed_eq<B>(crow ^ (crow >> B)) & hmask) : 0u;        // equal to the right neighbour
-            const uint32_t H3 = e & (e >> B);                                               // starts of horizontal triples
-            const uint32_t V = (in && lane >= 2) ? (packed_eq<B>(crow ^ cu1) & packed_eq<B>(cu1 ^ cu2) & cmask) : 0u;   // bottoms of vertical triples
-            const uint32_t Nn = in ? (packed_eq<B>(trow ^ cells) & cmask) : 0u;             // normal tiles (type 1)
-            const unsigned has = ballot((H3 | V) != 0u);
-            if (!has) { stable = true; break; }
-            const int rs = 31 - __clz((int)has);                                            // bottom-most row with a candidate line
-            const uint32_t Hrs = (uint32_t)shfl((int)H3, rs), Vrs = (uint32_t)shfl((int)V, rs);
-            if (Hrs && Vrs) break;                                                          // both kinds: general path
-            uint32_t dm = 0u, m3 = 0u, m4 = 0u, create = 0u;                                // column masks (low bit of the cell)
-            int laser = 0;
-            if (Hrs) {
-                // horizontal lines in row rs: cells, lengths, the second cell of every 4-line
-                const uint32_t ers = (uint32_t)shfl((int)e, rs), nrs = (uint32_t)shfl((int)Nn, rs);
-                const uint32_t hc = Hrs | (Hrs << B) | (Hrs << (2 * B));
-                const uint32_t q4 = ers & (ers >> B) & (ers >> (2 * B));                     // starts of runs of >= 4 cells
-                if ((q4 & (ers >> (3 * B))) != 0u || (hc & ~nrs) != 0u) break;              // a 5-line, or a tile that is not normal
-                laser = sp_h ? 3 : (sp_v ? 2 : 0);                                         // ref :297-302
-                create = laser ? (q4 << B) : 0u;
-                dm = hc & ~create;
-                n_new += __popc(create);
-                elim += __popc(dm);
-                if (lane == rs && create) {                                                // the laser keeps the line's colour (ref :596-597)
-                    const uint32_t f = create * 7u;
-                    trow = (trow & ~f) | (create * (uint32_t)laser);
-                }
-                const uint32_t f = dm * 7u;                                                // gravity: the rows above fall by one in these columns
-                const uint32_t tu1 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)trow, 1);
-                if (lane <= rs) {
-                    crow = (crow & ~f) | (lane >= 1 ? (cu1 & f) : 0u);
-                    trow = (trow & ~f) | (lane >= 1 ? (tu1 & f) : 0u);
-                }
-            } else {
-                // vertical lines ending in row rs: 3 long, or 4 if the cell above continues them; 5 -> general path
-                const uint32_t c_rs = (uint32_t)shfl((int)crow, rs);
-                const uint32_t same = in ? (packed_eq<B>(crow ^ c_rs) & Vrs) : 0u;          // my cell has the line's colour
-                const uint32_t v4 = rs >= 3 ? (uint32_t)shfl((int)same, rs - 3) : 0u;
-                const uint32_t v5 = rs >= 4 ? ((uint32_t)shfl((int)same, rs - 4) & v4) : 0u;
-                const uint32_t lc = (lane <= rs && lane >= rs - 2) ? Vrs : ((lane == rs - 3) ? v4 : 0u);   // my cells of the lines
-                // not simple: a 5-line, a tile that is not normal, or a line cell with an equal horizontal neighbour
-                // (it could start a crossing segment, ref :198-214)
-                if (ballot(v5 != 0u || (lc & ~Nn) != 0u || (lc & (e | (e << B))) != 0u)) break;
-                const uint32_t make = sp_v ? v4 : 0u;                                       // vertical 4-line -> vertical laser (ref :297-302)
-                m3 = (Vrs & ~v4) | make;                                                   // three cells go (the laser of a 4-line lands on row rs)
-                m4 = v4 & ~make;
-                n_new += __popc(make);
-                elim += 3 * __popc(m3) + 4 * __popc(m4);
-                const uint32_t cu3 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)crow, 3), cu4 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)crow, 4);
-                const uint32_t tu3 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)trow, 3), tu4 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)trow, 4);
-                if (lane <= rs) {
-                    const uint32_t k3 = (lane == rs ? (m3 & ~make) : m3) * 7u, k4 = m4 * 7u;
-                    crow = (crow & ~(k3 | k4)) | (lane >= 3 ? (cu3 & k3) : 0u) | (lane >= 4 ? (cu4 & k4) : 0u);
-                    trow = (trow & ~(k3 | k4)) | (lane >= 3 ? (tu3 & k3) : 0u) | (lane >= 4 ? (tu4 & k4) : 0u);
-                    if (lane == rs && make) trow = (trow & ~(make * 7u)) | (make * 2u);     // keeps its colour, becomes the laser
-                }
-            }
-            changed = true;
-            ++prof_rounds;
-            // ---- refill (ref :231-241): the k-th draw goes to the k-th empty cell in row-major order ----
-            const uint32_t em0 = dm | m3 | m4, em3 = m4;                                    // empty cells of rows 0..2 / row 3
-            const int n0 = __popc(em0), n3 = __popc(em3);
-            const int total = (m3 | m4) ? 3 * n0 + n3 : n0;
-            const uint32_t em = lane < 3 ? (lane == 0 || (m3 | m4) ? em0 : 0u) : (lane == 3 ? em3 : 0u);
-            int rank = (m3 | m4) ? (lane < 3 ? lane * n0 : 3 * n0) : 0;
-            const int off = (int)(dcur & 3ull);
-            const int nb = (off + total + 3) >> 2;                                          // <= L blocks (total <= 4 C)
-            sync();
-            if (!p.use_inj && lane < nb) {
-                uint32_t w[4];
-                const uint64_t blk = (dcur >> 2) + (uint64_t)lane;
-                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), gid, 0u, p.key0, p.key1, w);
-                *reinterpret_cast<uint4*>(&s.wbuf[4 * lane]) = *reinterpret_cast<uint4*>(w);
-            }
-            sync();
-            uint32_t m = (lane < 4) ? em : 0u;
-#pragma unroll 1
-            while (m) {
-                const int bit = __ffs((int)m) - 1;                                          // = 3 * column
-                m &= m - 1u;
-                const uint32_t v = p.use_inj ? (uint32_t)injected_colour(rank) : 1u + __umulhi(s.wbuf[off + rank], (uint32_t)K);
-                ++rank;
-                crow = (crow & ~(7u << bit)) | (v << bit);
-                trow = (trow & ~(7u << bit)) | (1u << bit);
-            }
-            dcur += (uint64_t)total;
-        }
-        // the board back as bytes
-        if (changed) {
-            sync();
-            if (lane < RR) {
-#pragma unroll
-                for (int c = 0; c < CC; ++c) {
-                    const int t = (int)((trow >> (c * B)) & 7u);
-                    col[lane * CC + c] = (int8_t)((crow >> (c * B)) & 7u);
-                    typ[lane * CC + c] = (int8_t)(t == 7 ? -1 : t);
-                }
-            }
-            sync();
-        }
-        return stable;
-    }
-
     // move (ref :330-378) after the effectiveness gate, in the pieces the kernels schedule:
     // move_begin = counters, swap and the combination match (ref :343-361), returns is_combination_match -- its
     // gravity + refill (ref :362-364) is left to the first cascade_trip; cascade_trip = one trip of the cascade
@@ -2237,12 +2096,8 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             b.action_cells((int)(packed & IT_ACTION), i1, i2);
             bool pending_fall = b.move_begin(i1, i2);
             is_comb = pending_fall;
-            bool stable = false;
-            if (Board<L, RT, CT>::PACKED_ROUNDS && !pending_fall && p.K <= 7) stable = b.packed_cascade(elim);   // the simple rounds
-            if (!stable) {
 #pragma unroll 1
-                while (b.cascade_trip(pending_fall, elim)) {}
-            }
+            while (b.cascade_trip(pending_fall, elim)) {}
         }
         finish_item<L, RT, CT>(b, p, packed, elim, is_comb, prof_t0);
     }
