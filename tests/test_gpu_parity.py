@@ -314,6 +314,33 @@ def test_step_many_equals_single_steps(R, Cc, K, moves, autoreset, T):
         assert_same(g, o, f"single step after window {window}")
 
 
+def test_full_occupancy_batch_matches_oracle_across_episode_boundaries():
+    """BASELINE configs[1] at its full size: 65 536 envs, every buffer compared with the oracle while the persistent
+    kernels are fully occupied, the work list is long, and every env crosses an episode boundary (pool hand-over);
+    then one 30-step rollout on top."""
+    torch = _torch()
+    N, R, Cc, K, moves = 65536, 10, 10, 4, 30
+    g = GpuAdapter(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=2, autoreset="same_step"))
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=2, autoreset="same_step", num_threads=os.cpu_count() or 8)
+    g.env.reset(); o.reset()
+    assert_same(g, o, "reset")
+    rng = np.random.default_rng(77)
+    for t in range(34):
+        a = rng.integers(0, o.A, size=N).astype(np.int32)
+        g.step(a); o.step(a)
+        if t in (0, 13, 28, 29, 30, 33):
+            assert_same(g, o, f"step {t}")
+        else:
+            assert np.array_equal(g.reward, o.reward) and np.array_equal(g.terminated, o.terminated), t
+    acts = rng.integers(0, o.A, (30, N)).astype(np.int32)
+    rew, term = g.env.step_many(torch.from_numpy(acts).cuda())
+    rew, term = rew.cpu().numpy(), term.cpu().numpy()
+    for t in range(30):
+        o.step(acts[t])
+        assert np.array_equal(rew[t], o.reward) and np.array_equal(term[t].astype(np.uint8), o.terminated), t
+    assert_same(g, o, "after the rollout")
+
+
 def test_checkpoint_resume_reproduces_the_trajectory():
     """state_dict / load_state_dict: an env resumed from a checkpoint -- the same handle or a fresh one --
     continues bit for bit like the original, including the boards of later episodes and a bound host mirror."""
