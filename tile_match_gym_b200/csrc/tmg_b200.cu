@@ -436,8 +436,10 @@ int tmg_step_many(tmg_env* e, const int32_t* actions_dev, int32_t num_steps, int
     p.ro_terminated = terminated_dev;
     p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // No wait for the pool refills in flight: k_rollout takes a pool entry only if its episode number says it is complete
-    // (published last by k_pregen) and generates the board itself otherwise -- the same bytes either way.
+    // No wait for the recent pool refills: k_rollout takes a pool entry only if its episode number says it is complete
+    // (published last by k_pregen) and generates the board itself otherwise -- the same bytes either way.  Refills of
+    // 24 or more launches ago are waited for, so that their range / event slots (rings of PG_RING) can be reused.
+    if (e->pregen && !wait_pregen(e, st, e->pregen_count - 24)) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
