@@ -240,6 +240,16 @@ def main():
     r1.record(stream)
     barrier()
     rollout_ms = r0.elapsed_time(r1)
+    # the agent inside the kernel: samples from the effective actions (every step is a move: ~4x the cascade work)
+    env.rollout(T, "mask"); env.join()
+    barrier()
+    r0.record(stream)
+    for i in range(n_win):
+        env.rollout(T, "mask")
+    env.join()
+    r1.record(stream)
+    barrier()
+    rollout_mask_ms = r0.elapsed_time(r1)
     status_bad += int((env.status != 0).sum().item())
 
     # ---- end-to-end timing through the host-buffer call (pinned host memory in and out) -----------------------
@@ -283,9 +293,9 @@ def main():
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms, rollout_mask_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms = t.tolist()
+        total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms, rollout_mask_ms = t.tolist()
         bad = torch.tensor([status_bad], device=dev); dist.all_reduce(bad); status_bad = int(bad.item())
     n_global = n_local * world
     value = n_global * args.steps / (total_ms * 1e-3)
@@ -316,7 +326,10 @@ def main():
                          "note": "integer/divergence-bound kernel: the HBM fraction is low by construction, see DESIGN.md"},
             "rollout": {"value": n_global * T * n_win / (rollout_ms * 1e-3), "unit": UNIT, "steps_per_launch": T, "launches": n_win,
                         "what": "tmg_step_many: the same env-steps with the actions of a whole window given up front "
-                                "(random-agent loop), boards kept on chip between steps; not the headline"},
+                                "(random-agent loop), boards kept on chip between steps; not the headline",
+                        "mask_policy_in_kernel": {"value": n_global * T * n_win / (rollout_mask_ms * 1e-3),
+                                                  "what": "tmg_rollout_policy(TMG_POLICY_MASK): actions sampled from the legal-move "
+                                                          "mask inside the kernel, every step an effective move"}},
             "clocks": clocks,
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "drain_ms": drain_ms, "wall_s": t_wall, "status_flags_set": status_bad,

@@ -159,6 +159,19 @@ int tmg_step(tmg_env *env, const int32_t *actions_dev, void *stream);
 int tmg_step_many(tmg_env *env, const int32_t *actions_dev, int32_t num_steps, int32_t *rewards_dev,
                   uint8_t *terminated_dev, void *stream);
 
+/* Fused rollout with the agent inside the kernel (the random agent of src/examples/random_agent.py:12-31, or one that
+ * samples from info["effective_actions"], tile_match_env.py:118-124).  At a step of env e (global id g) on board number
+ * j with `timer` moves made, the action is decided by word k = j * num_moves + timer of the env's action stream,
+ * W(seed, g, 2, k) (see the draw-stream contract above):
+ *   TMG_POLICY_UNIFORM  action = mulhi32(W, A)
+ *   TMG_POLICY_MASK     the mulhi32(W, n)-th of the n effective actions in index order (uniform if n == 0)
+ * Steps that take no action (the reset step of TMG_AUTORESET_NEXT_STEP, a finished env) record action 0.
+ * actions_out_dev (int32 [num_steps][N] or NULL) receives the actions taken; everything else as tmg_step_many. */
+#define TMG_POLICY_UNIFORM 1
+#define TMG_POLICY_MASK 2
+int tmg_rollout_policy(tmg_env *env, int32_t policy, int32_t num_steps, int32_t *actions_out_dev, int32_t *rewards_dev,
+                       uint8_t *terminated_dev, void *stream);
+
 /* recompute buffers.mask from the current boards (e.g. after the caller edited boards in place) */
 int tmg_legal_mask(tmg_env *env, void *stream);
 

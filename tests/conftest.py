@@ -27,3 +27,21 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(pytest.mark.skip(reason="reference tree not present on this machine"))
         if "gpu" in item.keywords and not have_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device"))
+
+
+import numpy as np  # noqa: E402
+
+
+def expected_policy_actions(o, seed, env_id_offset, num_moves, policy):
+    """The action tmg_rollout_policy must take for every env of the oracle's current state (include/tmg_b200.h)."""
+    from oracle.stream import mulhi32, stream_words
+    out = np.zeros(o.N, np.int32)
+    for e in range(o.N):
+        t = int(o.timer[e])
+        if t < 0 or t >= num_moves:
+            continue                                   # no action is taken (recorded as 0)
+        k = int(o.episode[e]) * num_moves + t
+        w = stream_words(seed, env_id_offset + e, 2, k, 1)
+        idx = np.flatnonzero(o.mask[e]) if policy == "mask" else np.arange(0)
+        out[e] = idx[int(mulhi32(w, len(idx))[0])] if len(idx) else int(mulhi32(w, o.A)[0])
+    return out

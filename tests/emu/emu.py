@@ -51,7 +51,7 @@ def lib():
         L.emu_set_injected_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.emu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_void_p]
-        L.emu_step_many.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.emu_step_many.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.emu_legal_mask.argtypes = [C.c_void_p]
         L.emu_debug_op.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -120,8 +120,13 @@ class EmuVecEnv:
         a = np.ascontiguousarray(actions, dtype=np.int32)
         T = a.shape[0]
         rew = np.zeros((T, self.N), np.int32); term = np.zeros((T, self.N), np.uint8)
-        self.L.emu_step_many(self.h, _ptr(a), T, _ptr(rew), _ptr(term))
+        self.L.emu_step_many(self.h, _ptr(a), T, _ptr(rew), _ptr(term), 0, None)
         return rew, term
+
+    def rollout(self, T, policy):
+        act = np.zeros((T, self.N), np.int32); rew = np.zeros((T, self.N), np.int32); term = np.zeros((T, self.N), np.uint8)
+        self.L.emu_step_many(self.h, None, T, _ptr(rew), _ptr(term), {"uniform": 1, "mask": 2}[policy], _ptr(act))
+        return act, rew, term
 
     def legal_mask(self):
         self.L.emu_legal_mask(self.h)

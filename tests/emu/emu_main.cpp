@@ -265,9 +265,10 @@ void emu_step(void* h, const int32_t* actions) {
         DISPATCH(e_pregen)
     }
 }
-void emu_step_many(void* h, const int32_t* actions, int T, int32_t* rewards, uint8_t* terminated) {
+void emu_step_many(void* h, const int32_t* actions, int T, int32_t* rewards, uint8_t* terminated, int policy, int32_t* actions_out) {
     EmuEnv* e = (EmuEnv*)h;
     g_params = e->p; g_params.actions = actions; g_params.T = T; g_params.ro_reward = rewards; g_params.ro_terminated = terminated;
+    g_params.policy = policy; g_params.ro_actions = actions_out;
     g_params.pool_tag = e->tag;
     DISPATCH(e_rollout)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {

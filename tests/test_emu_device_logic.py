@@ -6,6 +6,7 @@ import pytest
 
 from oracle import oracle as orc
 from test_oracle_golden import _trace_meta, replay_trace
+from conftest import expected_policy_actions
 from emu.emu import EmuVecEnv
 
 ALL_CL = ("cookie",)
@@ -43,6 +44,26 @@ def test_emulated_batch_vs_oracle(cfg):
         e.step(a); o.step(a)
         for f in fields:
             assert np.array_equal(getattr(e, f), getattr(o, f)), (t, f)
+
+
+@pytest.mark.parametrize("R,C,K,moves,autoreset,policy", [(10, 10, 4, 5, "same_step", "mask"), (9, 9, 6, 4, "next_step", "mask"),
+                                                         (10, 10, 4, 7, "same_step", "uniform"), (5, 6, 3, 4, "disabled", "mask")])
+def test_emulated_policy_rollout(R, C, K, moves, autoreset, policy):
+    """tmg_rollout_policy: the agent inside the kernel takes exactly the actions its stream contract says, and the
+    trajectory is the oracle's under those actions."""
+    N, T, seed, off = 16, 11, 8, 21
+    e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=seed, autoreset=autoreset, env_id_offset=off)
+    o = orc.OracleVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=seed, autoreset=autoreset, env_id_offset=off, num_threads=4)
+    e.reset(); o.reset()
+    for window in range(2):
+        act, rew, term = e.rollout(T, policy)
+        for t in range(T):
+            want = expected_policy_actions(o, seed, off, moves, policy)
+            assert np.array_equal(act[t], want), (window, t)
+            o.step(want)
+            assert np.array_equal(rew[t], o.reward) and np.array_equal(term[t], o.terminated), (window, t)
+        for f in ("board", "timer", "mask", "episode", "draw_cursor", "status", "reward", "num_moves_left"):
+            assert np.array_equal(getattr(e, f), getattr(o, f)), (window, f)
 
 
 @pytest.mark.parametrize("R,C,K,cap", [(10, 10, 4, 6), (9, 9, 6, 2), (6, 7, 3, 4)])

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, expected_policy_actions
 from oracle import oracle as orc
 from test_oracle_golden import _trace_meta, replay_trace, _draws, _split_specials
 
@@ -312,6 +312,30 @@ def test_step_many_equals_single_steps(R, Cc, K, moves, autoreset, T):
         a = rng.integers(0, o.A, N).astype(np.int32)
         g.step(a); o.step(a)
         assert_same(g, o, f"single step after window {window}")
+
+
+@pytest.mark.parametrize("R,Cc,K,moves,autoreset,policy", [(10, 10, 4, 30, "same_step", "mask"), (9, 9, 6, 5, "next_step", "mask"),
+                                                          (10, 10, 4, 8, "same_step", "uniform"), (7, 9, 5, 6, "disabled", "mask")])
+def test_policy_rollout_takes_the_contract_actions(R, Cc, K, moves, autoreset, policy):
+    """tmg_rollout_policy: the agent inside the kernel takes exactly the actions its stream contract says (word
+    board*num_moves + timer of stream 2; uniform, or the n-th effective action), and the trajectory is the oracle's."""
+    N, T, seed, off = 600, 2 * moves + 3 if moves < 30 else 33, 31, 1000
+    env = make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=seed, autoreset=autoreset, env_id_offset=off)
+    g = GpuAdapter(env)
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=seed, autoreset=autoreset, env_id_offset=off, num_threads=8)
+    env.reset(); o.reset()
+    act, rew, term = env.rollout(T, policy)
+    act, rew, term = act.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy().astype(np.uint8)
+    n_eff = 0
+    for t in range(T):
+        want = expected_policy_actions(o, seed, off, moves, policy)
+        assert np.array_equal(act[t], want), t
+        o.step(want)
+        assert np.array_equal(rew[t], o.reward) and np.array_equal(term[t], o.terminated), t
+        n_eff += int((o.reward > 0).sum())
+    assert_same(g, o, "after the policy rollout")
+    if policy == "mask" and autoreset == "same_step":
+        assert n_eff == N * T          # every sampled action is effective
 
 
 def test_full_occupancy_batch_matches_oracle_across_episode_boundaries():

@@ -21,6 +21,7 @@ SPECIAL_BITS = {"cookie": SP_COOKIE, "vertical_laser": SP_VERTICAL_LASER,
                 "horizontal_laser": SP_HORIZONTAL_LASER, "bomb": SP_BOMB}
 AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
 REFILL = {"philox": 0, "injected": 1}
+POLICY = {"uniform": 1, "mask": 2}
 FLAG_NO_MASK = 1
 FLAG_NO_PREGEN = 2
 
@@ -70,6 +71,7 @@ EXPORTS = {
     "tmg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_step_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_rollout_policy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_legal_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -424,14 +424,16 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
     return launch_pregen(e, st);
 }
 
-int tmg_step_many(tmg_env* e, const int32_t* actions_dev, int32_t num_steps, int32_t* rewards_dev, uint8_t* terminated_dev,
-                  void* stream) {
-    if (!e || !actions_dev || num_steps < 0) return TMG_ERR_INVALID_ARG;
+static int rollout(tmg_env* e, int policy, const int32_t* actions_dev, int32_t num_steps, int32_t* actions_out_dev,
+                   int32_t* rewards_dev, uint8_t* terminated_dev, void* stream) {
+    if (!e || num_steps < 0) return TMG_ERR_INVALID_ARG;
     if (num_steps == 0) return TMG_OK;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     Params p = e->p;
     p.actions = actions_dev;
+    p.policy = policy;
     p.T = num_steps;
+    p.ro_actions = actions_out_dev;
     p.ro_reward = rewards_dev;
     p.ro_terminated = terminated_dev;
     p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
@@ -450,6 +452,18 @@ int tmg_step_many(tmg_env* e, const int32_t* actions_dev, int32_t num_steps, int
     });
     if (rc != TMG_OK) return rc;
     return launch_pregen(e, st);
+}
+
+int tmg_step_many(tmg_env* e, const int32_t* actions_dev, int32_t num_steps, int32_t* rewards_dev, uint8_t* terminated_dev,
+                  void* stream) {
+    if (!actions_dev) return TMG_ERR_INVALID_ARG;
+    return rollout(e, POLICY_GIVEN, actions_dev, num_steps, nullptr, rewards_dev, terminated_dev, stream);
+}
+
+int tmg_rollout_policy(tmg_env* e, int32_t policy, int32_t num_steps, int32_t* actions_out_dev, int32_t* rewards_dev,
+                       uint8_t* terminated_dev, void* stream) {
+    if (policy != TMG_POLICY_UNIFORM && policy != TMG_POLICY_MASK) return TMG_ERR_INVALID_ARG;
+    return rollout(e, policy, nullptr, num_steps, actions_out_dev, rewards_dev, terminated_dev, stream);
 }
 
 int tmg_legal_mask(tmg_env* e, void* stream) {

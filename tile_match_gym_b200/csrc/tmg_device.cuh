@@ -61,6 +61,7 @@ enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 
 enum : uint32_t { FLAG_NO_MASK = 1u, FLAG_NO_PREGEN = 2u };
 enum { OP_GRAVITY = 1, OP_REFILL, OP_RESOLVE_ROUND, OP_ACTIVATE, OP_COMBINE, OP_MOVE, OP_EFFECTIVE, OP_GENERATE,
        OP_SHUFFLE, OP_COUNT_LINES };
+enum { POLICY_GIVEN = 0, POLICY_UNIFORM = 1, POLICY_MASK = 2 };
 enum { NAME_NORMAL = 0, NAME_VLASER = 2, NAME_HLASER = 3, NAME_BOMB = 4, NAME_COOKIE = -1 };  // = created tile type
 
 struct Params {
@@ -116,6 +117,8 @@ struct Params {
     int T;                   // tmg_step_many: steps in this call; actions is [T][N]
     int32_t* ro_reward;      // [T][N] or NULL
     uint8_t* ro_terminated;  // [T][N] or NULL
+    int32_t* ro_actions;     // [T][N] or NULL: the actions taken (on-device policies)
+    int policy;              // 0: actions given; POLICY_UNIFORM / POLICY_MASK: drawn inside the kernel from stream 2
     const int32_t* dbg_args;
     int dbg_op;
     uint32_t* prof;  // optional [N][8]: cycles total, cycles in the general path, cascade rounds, redraw iterations,
@@ -2125,12 +2128,43 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         unsigned effv = 0u, effh = 0u;
         bool have_mask = false, regenerated = false, pool_used = false, touched = false;
         int reward = 0, is_comb = 0, shuffled = 0, terminated = 0, n_new = 0, n_act = 0;
+        uint32_t aw[4] = {0u, 0u, 0u, 0u};          // on-device policy: the Philox block of the action stream in use
+        uint64_t aw_blk = ~0ull;
 #pragma unroll 1
         for (int t = 0; t < p.T; ++t) {
-            const int action = p.actions[(size_t)t * p.N + env];
+            int action = p.policy ? 0 : p.actions[(size_t)t * p.N + env];
             reward = 0; is_comb = 0; shuffled = 0; terminated = 0; n_new = 0; n_act = 0;
             bool eff = false, regenerate = false, fault = false;
-            if (timer < 0 || timer >= p.num_moves) {
+            const bool live = !(timer < 0 || timer >= p.num_moves);
+            if (live && p.policy) {
+                // The agent of src/examples/random_agent.py:12-31 inside the kernel.  Word k = board number * num_moves
+                // + timer of the env's action stream (stream 2) decides: uniform over all actions, or the
+                // mulhi32(word, n)-th of the n effective actions in index order (ref tile_match_env.py:118-124).
+                if (!have_mask) { b.mask_bits(effv, effh); have_mask = true; }
+                const uint64_t k = (uint64_t)(unsigned)episode * (uint64_t)p.num_moves + (uint64_t)timer;
+                if ((k >> 2) != aw_blk) {
+                    aw_blk = k >> 2;
+                    philox4x32_10((uint32_t)aw_blk, (uint32_t)(aw_blk >> 32), b.gid, 2u, p.key0, p.key1, aw);
+                }
+                const uint32_t word = (k & 3) == 0 ? aw[0] : (k & 3) == 1 ? aw[1] : (k & 3) == 2 ? aw[2] : aw[3];
+                const int n_eff = p.policy == POLICY_MASK ? b.radd(__popc(effv) + __popc(effh)) : 0;
+                if (n_eff == 0) action = (int)__umulhi(word, (uint32_t)p.A);
+                else {
+                    int kth = (int)__umulhi(word, (uint32_t)n_eff);
+                    action = -1;
+#pragma unroll 1
+                    for (int r = 0; r < 2 * b.R && action < 0; ++r) {             // vertical actions row by row, then horizontal
+                        const bool vert = r < b.R;
+                        const int rr = vert ? r : r - b.R;
+                        const unsigned m = b.ballot(((vert ? effv : effh) >> rr) & 1u);
+                        const int c = __popc(m);
+                        if (kth < c) action = (vert ? rr * b.C : b.C * (b.R - 1) + rr * (b.C - 1)) + b.nth_bit(m, kth);
+                        else kth -= c;
+                    }
+                }
+            }
+            if (p.ro_actions && lane == 0) p.ro_actions[(size_t)t * p.N + env] = action;
+            if (!live) {
                 if (p.autoreset == AUTORESET_NEXT_STEP && timer >= p.num_moves) regenerate = true;   // this step is the reset
                 else { b.status |= ST_NEEDS_RESET; fault = true; }                                  // ref tile_match_env.py:94-95
             } else if (action < 0 || action >= p.A) {                                               // ref tile_match_env.py:97

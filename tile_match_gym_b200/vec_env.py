@@ -288,6 +288,19 @@ class TileMatchVecEnv:
         self._last_actions = a
         return rew, term.view(torch.bool)
 
+    def rollout(self, num_steps: int, policy: str = "mask"):
+        """num_steps steps with the agent inside the kernel (tmg_rollout_policy): policy "uniform" draws any action,
+        "mask" samples from the effective actions.  Returns (actions (T, N) int32, rewards (T, N) int32,
+        terminations (T, N) bool); the actions are a pure function of (seed, env id, board number, timer)."""
+        T = int(num_steps)
+        act = torch.empty((T, self.num_envs), dtype=torch.int32, device=self.device)
+        rew = torch.empty((T, self.num_envs), dtype=torch.int32, device=self.device)
+        term = torch.empty((T, self.num_envs), dtype=torch.uint8, device=self.device)
+        nat.check(self._lib.tmg_rollout_policy(self._h, nat.POLICY[policy], T, C.c_void_p(act.data_ptr()),
+                                               C.c_void_p(rew.data_ptr()), C.c_void_p(term.data_ptr()), self._stream()),
+                  "tmg_rollout_policy")
+        return act, rew, term.view(torch.bool)
+
     def join(self) -> None:
         """Make the current stream wait for the board generations queued on the library's side stream."""
         nat.check(self._lib.tmg_join(self._h, self._stream()), "tmg_join")
