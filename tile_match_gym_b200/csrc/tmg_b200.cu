@@ -27,6 +27,8 @@ struct tmg_env {
     cudaStream_t side[SIDE];
     cudaEvent_t ev_step, ev_pregen[RING];
     long long pregen_count;   // number of k_pregen launches so far
+    cudaStream_t waited_stream;           // the caller stream of the last wait_pregen ...
+    long long waited_tag[SIDE];           // ... and the latest tag of each side stream it has waited for
     long long step_count;     // number of tmg_step calls so far (parity selects the work-list counters)
     int persistent_blocks;    // resident-block slots of the device for k_work / k_pregen (persistent groups)
     int pregen_grid_cap;      // diagnostics: cap on the blocks of a k_pregen launch
@@ -90,14 +92,21 @@ template <int L> int grid_for(int n) { return (n + Cfg<L>::GPB - 1) / Cfg<L>::GP
 
 }  // namespace
 
-// `st` waits until every k_pregen launch with tag <= upto has finished (one wait per side stream)
+// `st` waits until every k_pregen launch with tag <= upto has finished: one wait per side stream, and only for
+// streams whose latest such launch this stream has not waited for already (a step usually adds one new tag)
 static bool wait_pregen(tmg_env* e, cudaStream_t st, long long upto) {
     if (!e->pregen) return true;
+    if (st != e->waited_stream) {           // another caller stream: it has waited for nothing yet
+        e->waited_stream = st;
+        for (int s = 0; s < tmg_env::SIDE; ++s) e->waited_tag[s] = -1;
+    }
     for (int s = 0; s < tmg_env::SIDE; ++s) {
         if (upto < s) continue;
         const long long j = upto - ((upto - s) % tmg_env::SIDE);   // latest tag <= upto on side stream s
+        if (j <= e->waited_tag[s]) continue;
         // (if that slot was reused by a later launch of the same stream the wait is only stronger)
         if (cudaStreamWaitEvent(st, e->ev_pregen[j % tmg_env::RING], 0) != cudaSuccess) return false;
+        e->waited_tag[s] = j;
     }
     return true;
 }
@@ -262,6 +271,8 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     e->mask_bits_dev = reinterpret_cast<uint8_t*>(b + o_mask_bits);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
+    e->waited_stream = nullptr;
+    for (int i = 0; i < tmg_env::SIDE; ++i) e->waited_tag[i] = -1;
     e->step_count = 0;
     e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr; e->hm_terminated = nullptr;
     e->hm_reward = nullptr; e->hm_moves_left = nullptr; e->hm_bound = false;
