@@ -1262,8 +1262,12 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         if (sc.hs == 0u) {                                   // vertical lines only
             const int len = sc.has_v ? rs - sc.vtop + 1 : 0;
             const unsigned vrows = sc.has_v ? ((2u << rs) - 1u) & ~((1u << sc.vtop) - 1u) : 0u;
-            // a cell of the line with an equal horizontal neighbour could start a phase-2 segment (ref :198-214)
-            if (ballot((vrows & (b.S | b.E | El)) != 0u || len > 4)) return 0;
+            // a phase-2 segment (ref :198-214) is a horizontal run of >= 3 equal cells through a cell of the line: the cell
+            // with the two to its right, with one on either side, or with the two to its left.  (Ignoring the type and
+            // phase-1 cuts of :199-209 only makes the test stricter.)
+            const unsigned Er = from_right(b.E, 1), Ell = from_left(El, 1);
+            const unsigned cross = (b.E & Er) | (El & b.E) | (Ell & El);
+            if (ballot((vrows & (b.S | cross)) != 0u || len > 4)) return 0;
             const bool make = sc.has_v && len == 4 && sp_v;                   // vertical 4-line -> vertical laser or normal
             if (DEFER_GAPS) {
                 // the laser is created on the second cell (ref :453-456) and falls to the anchor row: write it there
