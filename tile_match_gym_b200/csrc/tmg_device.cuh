@@ -1232,60 +1232,58 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         n_new += ncq;
     }
 
-    // Fast path of a cascade round (most rounds): the lines anchored on row r* are all 3 or 4 long, pairwise disjoint,
-    // contain no special tile and have no crossing segments.  Then process_colour_lines yields one normal / laser
+    // Fast path of a cascade round (most rounds): the lines anchored on row r* -- horizontal, vertical or both -- are all
+    // 3 or 4 long, pairwise disjoint, contain no special tile and have no crossing segments.  Then process_colour_lines yields one normal / laser
     // match per line (ref :294-302,322-325), nothing is activated, deletions commute, and the creation cell of a
     // 4-line is its second cell (ref :453-456).  Returns the number of lines, or 0 if the general path must run.
     __device__ __forceinline__ int fast_round(const Scan& sc) {
         const Bits& b = sc.bits;
         const int rs = sc.rstar;
         const bool sp_v = specials & SP_VLASER, sp_h = specials & SP_HLASER;
-        const unsigned El = from_left(b.E, 1);               // bit r: my left neighbour has my colour
-        if (sc.mv == 0u) {                                   // horizontal lines only
-            const bool mine = (sc.hcells >> lane) & 1u;
-            const bool start = (sc.hs >> lane) & 1u;
-            const int len = start ? __ffs((int)~(sc.m >> lane)) : 0;          // run + 1
-            const unsigned long4 = ballot(start && len == 4);
-            if (ballot((mine && ((b.S >> rs) & 1u)) || len > 4)) return 0;
-            const int laser = sp_h ? 3 : (sp_v ? 2 : 0);                      // ref :297-302
-            const unsigned create = laser ? (long4 << 1) : 0u;               // second cell of each 4-line
-            if (DEFER_GAPS) { fg_len = 0; fg_valid = true; }
-            if (mine) {
-                const int i = rs * C + lane;
-                if ((create >> lane) & 1u) typ[i] = (int8_t)laser;           // keeps the line's colour (ref :596-597)
-                else if (DEFER_GAPS) { fg_top = rs; fg_len = 1; }
-                else { col[i] = 0; typ[i] = 0; }
-            }
-            n_new += __popc(create);
-            return __popc(sc.hs);
-        }
-        if (sc.hs == 0u) {                                   // vertical lines only
-            const int len = sc.has_v ? rs - sc.vtop + 1 : 0;
+        // horizontal lines of row rs
+        const bool mine = (sc.hcells >> lane) & 1u;
+        const bool start = (sc.hs >> lane) & 1u;
+        const int hlen = start ? __ffs((int)~(sc.m >> lane)) : 0;             // run + 1
+        bool bad = (mine && ((b.S >> rs) & 1u)) || hlen > 4;
+        // vertical lines anchored on row rs.  A phase-2 segment (ref :198-214) is a horizontal run of >= 3 equal cells
+        // through a cell of such a line: the cell with the two to its right, with one on either side, or with the two
+        // to its left (ignoring the type and phase-1 cuts of :199-209 only makes the test stricter).  It also covers a
+        // horizontal line of row rs that shares its cell with the vertical line, so the lines that pass are disjoint.
+        const int vlen = sc.has_v ? rs - sc.vtop + 1 : 0;
+        if (sc.mv) {
             const unsigned vrows = sc.has_v ? ((2u << rs) - 1u) & ~((1u << sc.vtop) - 1u) : 0u;
-            // a phase-2 segment (ref :198-214) is a horizontal run of >= 3 equal cells through a cell of the line: the cell
-            // with the two to its right, with one on either side, or with the two to its left.  (Ignoring the type and
-            // phase-1 cuts of :199-209 only makes the test stricter.)
-            const unsigned Er = from_right(b.E, 1), Ell = from_left(El, 1);
+            const unsigned El = from_left(b.E, 1), Er = from_right(b.E, 1), Ell = from_left(El, 1);
             const unsigned cross = (b.E & Er) | (El & b.E) | (Ell & El);
-            if (ballot((vrows & (b.S | cross)) != 0u || len > 4)) return 0;
-            const bool make = sc.has_v && len == 4 && sp_v;                   // vertical 4-line -> vertical laser or normal
+            bad = bad || (vrows & (b.S | cross)) != 0u || vlen > 4;
+        }
+        if (ballot(bad)) return 0;
+        // every line is 3 or 4 normal tiles and no two share a cell: one match per line, in any order
+        const int laser = sp_h ? 3 : (sp_v ? 2 : 0);                          // horizontal 4-line (ref :297-302)
+        const unsigned create = (laser && sc.hs) ? (ballot(start && hlen == 4) << 1) : 0u;   // its second cell (ref :453-456)
+        const bool make = sc.has_v && vlen == 4 && sp_v;                      // vertical 4-line -> vertical laser or normal
+        if (DEFER_GAPS) { fg_len = 0; fg_valid = true; }
+        if (mine) {
+            const int i = rs * C + lane;
+            if ((create >> lane) & 1u) typ[i] = (int8_t)laser;               // keeps the line's colour (ref :596-597)
+            else if (DEFER_GAPS) { fg_top = rs; fg_len = 1; }
+            else { col[i] = 0; typ[i] = 0; }
+        }
+        if (sc.has_v) {
             if (DEFER_GAPS) {
                 // the laser is created on the second cell (ref :453-456) and falls to the anchor row: write it there
-                fg_valid = true;
                 fg_top = sc.vtop;
-                fg_len = sc.has_v ? (make ? len - 1 : len) : 0;
+                fg_len = make ? vlen - 1 : vlen;
                 if (make) typ[rs * C + lane] = 2;
-            } else if (sc.has_v) {
+            } else {
                 for (int r = sc.vtop; r <= rs; ++r) {
                     const int i = r * C + lane;
                     if (make && r == sc.vtop + 1) typ[i] = 2;
                     else { col[i] = 0; typ[i] = 0; }
                 }
             }
-            n_new += __popc(ballot(make));
-            return __popc(sc.mv);
         }
-        return 0;
+        n_new += __popc(create) + (sc.mv ? __popc(ballot(make)) : 0);
+        return __popc(sc.hs) + __popc(sc.mv);
     }
 
     // general path of a cascade round: line table, classification, resolution with activations
