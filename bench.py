@@ -39,9 +39,9 @@ P = ROWS * COLS
 A = 2 * P - ROWS - COLS
 # algorithmic bytes per env-step = 4P + 48 + A = 628 B for 10x10 (int8 planes in+out, scalars, mask)
 BYTES_PER_STEP = 4 * P + 48 + A
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch (ncu --set full, profiles/r01d_k_work_ncu.txt):
-# 5.83 MB read + 0.28 MB written (no-op steps never load their board; writes stay in the 126 MB L2 within a launch)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 6.11e6
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch (ncu --set full, profiles/r01e_k_work_ncu.txt):
+# 5.84 MB read + 0.22 MB written (no-op steps never load their board; writes stay in the 126 MB L2 within a launch)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 6.07e6
 METRIC = "env-steps/sec (full cascade, bit-exact)"
 UNIT = "env-steps/s"
 
