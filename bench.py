@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0, period=0.05):
+    def __init__(self, index=0, period=0.1):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.stop_flag = index, period, [], threading.Event()
 
@@ -202,7 +202,11 @@ def main():
     # ---- device-resident timing: CUDA events around every tmg_step launch, L2 flushed in between -------------
     for i in range(args.warmup):
         env.step(actions[i % n_act])
-    sampler = ClockSampler(local_rank); sampler.start()
+    # rank 0 samples its own GPU's clocks (every rank spawning nvidia-smi in a loop would load the host cores that
+    # the end-to-end path runs on)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     env.join()   # start from an empty side stream so that the timed region owns all of its board generations
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -289,7 +293,7 @@ def main():
     hs, e2e_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"), mirror=True)
     hs_full, e2e_full_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"))
     hs_bytes, e2e_bytes_ms = time_host_path(("board", "reward", "terminated", "mask", "num_moves_left"))
-    clocks = sampler.summary()
+    clocks = sampler.summary() if rank == 0 else None
 
     # max over ranks
     if world > 1:
