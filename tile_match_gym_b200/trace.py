@@ -1,8 +1,9 @@
 """Trace / replay files: one `.npz` that holds everything needed to reproduce a stretch of play bit for
 bit -- the env configuration, the state the stretch starts from (`TileMatchVecEnv.state_dict()`), the actions, the
 injected draws if the env uses them, and what every step returned.  The same file is read by the GPU env
-(`replay_trace`, below) and by the CPU oracle (`oracle/trace.py`, test infrastructure), so a trajectory recorded on
-one side can be checked on the other; it also doubles as a checkpoint that carries its own proof.
+(`replay_trace`, below) and by the CPU checker of the test suite (which restates the key names instead of importing
+this module), so a trajectory recorded on one side can be checked on the other; it also doubles as a checkpoint that
+carries its own proof.
 
 What a step returns is what `TileMatchEnv.step` returns (tile_match_env.py:93-112): reward, done, the info counters,
 `num_moves_left`, plus -- optionally, they dominate the file size -- the board and the effective-action mask after the
