@@ -365,6 +365,23 @@ def test_full_occupancy_batch_matches_oracle_across_episode_boundaries():
     assert_same(g, o, "after the rollout")
 
 
+def test_many_episodes_stay_bit_exact():
+    """1 500 steps of 3-move episodes = 500 boards per env: the pool of boards generated ahead of time, its request ring
+    and its event slots wrap many times; every buffer still equals the oracle's (checked every 50 steps)."""
+    N, R, Cc, K, moves = 2048, 10, 10, 4, 3
+    g = GpuAdapter(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=5, autoreset="same_step", env_id_offset=1000))
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=5, autoreset="same_step", env_id_offset=1000, num_threads=8)
+    g.reset(); o.reset()
+    rng = np.random.default_rng(1)
+    for t in range(1500):
+        a = rng.integers(0, o.A, size=N).astype(np.int32)
+        g.step(a); o.step(a)
+        if t % 50 == 49 or t < 5:
+            assert_same(g, o, f"step {t}")
+    assert_same(g, o, "end")
+    assert int(o.episode.max()) == 500
+
+
 def test_checkpoint_resume_reproduces_the_trajectory():
     """state_dict / load_state_dict: an env resumed from a checkpoint -- the same handle or a fresh one --
     continues bit for bit like the original, including the boards of later episodes and a bound host mirror."""

@@ -143,7 +143,10 @@ enum {
     CTL_WL_COUNT_LO = CTL_RO_HEAD + 1,          // [2] normal-priority items (CTL_WL_COUNT counts the high-priority ones)
     CTL_WORDS = CTL_WL_COUNT_LO + 2
 };
-enum { PRI_SPECIALS = 4 };   // a move on a board with this many special tiles is scheduled first: 23 % of the effective
+#ifndef TMG_PRI_SPECIALS
+#define TMG_PRI_SPECIALS 4
+#endif
+enum { PRI_SPECIALS = TMG_PRI_SPECIALS };   // a move on a board with this many special tiles is scheduled first: 23 % of the effective
                              // moves, 80 % of the longest 1 % of the cascades (10x10, 4 colours, measured on the CPU restatement)
 enum : uint32_t { IT_ACTION = 0xfffu, IT_EFF = 1u << 12, IT_REGEN = 1u << 13, IT_ZERO_MASK = 1u << 14, IT_FROM_POOL = 1u << 15 };
 
