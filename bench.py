@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--num-moves", type=int, default=NUM_MOVES, help="diagnostic: episode length (huge = no resets)")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--step-stream-priority", type=int, default=0,
+                    help="diagnostic: run the steps on a CUDA stream of this priority (-1 = above the library's side streams)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -172,6 +174,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.step_stream_priority:
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.step_stream_priority))
     if world > 1:
         # keep stdout to the one JSON line: NCCL prints its version banner (and anything else) to stdout by default
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
