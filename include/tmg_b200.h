@@ -82,6 +82,8 @@ extern "C" {
 
 #define TMG_FLAG_NO_MASK 1u        /* do not maintain the legal-move mask in tmg_step / tmg_reset */
 #define TMG_FLAG_NO_PREGEN 2u      /* generate every board inside tmg_step instead of ahead of time on a side stream */
+#define TMG_FLAG_BYTE_PLANES 4u    /* run the moves on the byte planes in shared memory instead of the register-resident
+                                      bit-plane engine (same results; diagnostics / A-B measurements) */
 
 #define TMG_MAX_ROWS 32
 #define TMG_MAX_COLS 32
@@ -127,6 +129,8 @@ typedef struct tmg_buffers {
 } tmg_buffers;
 
 int tmg_abi_version(void);
+/* hash of the sources the library was built from (the Python loader rebuilds the library when it differs from the tree) */
+const char *tmg_build_id(void);
 const char *tmg_error_string(int code);
 /* "a|b|c" names of the TMG_ST_* bits set in `status` (static buffer per thread) */
 const char *tmg_status_string(uint32_t status);
@@ -236,7 +240,20 @@ int tmg_host_bind(tmg_env *env, const tmg_host_io *io, void *stream);
 #define TMG_OP_GENERATE 8       /* Board.generate_board                                       board.py:95-112 */
 #define TMG_OP_SHUFFLE 9        /* Board.shuffle                                              board.py:114-118 */
 #define TMG_OP_COUNT_LINES 10   /* len(get_colour_lines()) -> reward                          board.py:149-215 */
+#define TMG_OP_LINES 11         /* get_colour_lines() itself: see tmg_debug_lines                board.py:149-215 */
+#define TMG_OP_BYTE_PLANES 0x100 /* OR into `op`: run the primitive on the byte-plane implementation (boards of up to 10 rows
+                                    and 7 colours otherwise run it on the register-resident engine the step kernels use) */
 int tmg_debug_op(tmg_env *env, int32_t op, const int32_t *args_dev, void *stream);
+
+/* get_colour_lines() (board.py:149-215) of every env's board, as the engine's line table.  out_dev: device uint32
+ * [N][TMG_LINES_WORDS]: word 0 = number of lines n (at most 32 are reported), then n entries {info, cells}:
+ *   info  bits 0-11 position of the line in the reference's list (ascending = list order; values >= 1024 are the
+ *         crossing segments of board.py:198-214), bits 12-15 the row of the line's first cell, bit 16 kind
+ *         (0 horizontal, 1 vertical), bits 17-21 its row (horizontal) or column (vertical), bits 22-24 its colour;
+ *   cells bit set of the line's columns (horizontal) or rows (vertical).
+ * byte_planes != 0 reads the table of the byte-plane implementation instead of the register-resident engine's. */
+#define TMG_LINES_WORDS 65
+int tmg_debug_lines(tmg_env *env, uint32_t *out_dev, int32_t byte_planes, void *stream);
 
 /* Diagnostics: when set, every tmg_step writes per env {SM cycles spent, cycles in the general (non-fast) round path,
  * cascade rounds, redraw iterations} and ADDS the general path's cycles split into {scan, line table, classification,

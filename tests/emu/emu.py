@@ -38,7 +38,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(_HERE, "emu_main.cpp"), os.path.join(_HERE, "emu_shim.h"), _DEV]
+        srcs = [os.path.join(_HERE, "emu_main.cpp"), os.path.join(_HERE, "emu_shim.h"), _DEV, _DEV.replace("tmg_device.cuh", "tmg_rb.cuh")]
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-I", _HERE, "-o", _LIB,
                                    os.path.join(_HERE, "emu_main.cpp")])
@@ -54,6 +54,7 @@ def lib():
         L.emu_step_many.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.emu_legal_mask.argtypes = [C.c_void_p]
         L.emu_debug_op.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.emu_debug_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -134,3 +135,8 @@ class EmuVecEnv:
     def debug_op(self, op, args=None):
         a = None if args is None else np.ascontiguousarray(args, dtype=np.int32)
         self.L.emu_debug_op(self.h, op, None if a is None else _ptr(a))
+
+    def debug_lines(self, byte_planes=False):
+        out = np.zeros((self.N, 65), np.uint32)
+        self.L.emu_debug_lines(self.h, _ptr(out), int(byte_planes))
+        return out

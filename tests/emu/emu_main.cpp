@@ -108,6 +108,7 @@ static void run_group(int L, int first_tid, void (*fn)()) {
 using namespace tmg;
 
 static Params g_params;
+static bool rbk() { return rb_supported(32, g_params.R, g_params.K, g_params.flags); }
 template <int L> static void e_reset() {
     if (g_params.R == 10 && g_params.C == 10 && L == 32) k_reset<32, 10, 10>(g_params);
     else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_reset<32, 9, 9>(g_params);
@@ -115,10 +116,11 @@ template <int L> static void e_reset() {
     else k_reset<L, 0, 0>(g_params);
 }
 template <int L> static void e_step() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 32) k_work<32, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_work<32, 9, 9>(g_params);
-    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_work<32, 32, 32>(g_params);
-    else k_work<L, 0, 0>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) (rbk() ? k_work<32, 10, 10, true>(g_params) : k_work<32, 10, 10, false>(g_params));
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) (rbk() ? k_work<32, 9, 9, true>(g_params) : k_work<32, 9, 9, false>(g_params));
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_work<32, 32, 32, false>(g_params);
+    else if (rbk() && L == 32) k_work<L, 0, 0, true>(g_params);
+    else k_work<L, 0, 0, false>(g_params);
 }
 static void e_gate() { k_gate(g_params); }
 // one thread per env, whole warps (k_gate)
@@ -138,10 +140,11 @@ template <int L> static void e_pregen() {
     else k_pregen<L, 0, 0>(g_params);
 }
 template <int L> static void e_rollout() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 32) k_rollout<32, 10, 10>(g_params);
-    else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_rollout<32, 9, 9>(g_params);
-    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_rollout<32, 32, 32>(g_params);
-    else k_rollout<L, 0, 0>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) (rbk() ? k_rollout<32, 10, 10, true>(g_params) : k_rollout<32, 10, 10, false>(g_params));
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) (rbk() ? k_rollout<32, 9, 9, true>(g_params) : k_rollout<32, 9, 9, false>(g_params));
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_rollout<32, 32, 32, false>(g_params);
+    else if (rbk() && L == 32) k_rollout<L, 0, 0, true>(g_params);
+    else k_rollout<L, 0, 0, false>(g_params);
 }
 template <int L> static void e_mask() { k_mask<L>(g_params); }
 template <int L> static void e_debug() { k_debug<L>(g_params); }
@@ -161,6 +164,7 @@ struct EmuEnv {
     Params p;
     int L;
     int tag = 0, seq = 0;
+    int pregen_every = 1, since_pregen = 0;   // batches of pool requests: k_pregen after every `pregen_every` steps
     std::vector<char> mem;
 };
 
@@ -196,14 +200,15 @@ void* emu_create(const emu_config* c) {
     const bool fixed = (p.R == 10 && p.C == 10) || (p.R == 9 && p.C == 9);
     e->L = (p.R > 16 || fixed) ? 32 : (p.C <= 8 ? 8 : (p.C <= 10 ? 10 : (p.C <= 16 ? 16 : 32)));
     if (getenv("TMG_EMU_LANES32")) e->L = 32;
+    if (const char* pe = getenv("TMG_EMU_PREGEN_EVERY")) e->pregen_every = atoi(pe) > 0 ? atoi(pe) : 1;
     const size_t N = (size_t)p.N;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off = (off + b + 255) / 256 * 256; return o; };
     size_t cap = 1;
-    while (cap < N) cap <<= 1;
+    while (cap < 8 * N) cap <<= 1;
     size_t o[22] = {take(N * 2 * p.P), take(N * 4), take(N * 8), take(N * 8), take(N * 4), take(N), take(N), take(N * 4),
                     take(N * 4), take(N), take(N * p.A), take(N * 4), take(N * 4), take(N * 4), take(N * 4),
-                    take(N * 2 * p.P), take(N * p.A), take(N * 4), take(CTL_WORDS * 4), take(N * 8), take(cap * 4),
+                    take(N * 2 * p.P), take(N * p.A), take(N * 4), take(CTL_WORDS * 4), take(N * 8), take(cap * 8),
                     take(N)};
     e->mem.assign(off + 256, 0);
     char* b = e->mem.data();
@@ -217,7 +222,7 @@ void* emu_create(const emu_config* c) {
     p.pool_board = (int8_t*)(b + o[15]); p.pool_mask = (uint8_t*)(b + o[16]); p.pool_status = (uint32_t*)(b + o[17]);
     p.ctl = (uint32_t*)(b + o[18]); p.wl_items = (uint2*)(b + o[19]); p.req_mask = (uint32_t)(cap - 1);
     const bool pregen = !p.use_inj && !(p.flags & 2u) && p.autoreset != 0;
-    p.req_ring = pregen ? (int32_t*)(b + o[20]) : nullptr;
+    p.req_ring = pregen ? (uint2*)(b + o[20]) : nullptr;
     p.n_special = (uint8_t*)(b + o[21]);
     for (size_t i = 0; i < N; ++i) { p.timer[i] = -1; p.episode[i] = -1; p.pool_episode[i] = (int32_t)0x80808080; }
     return e;
@@ -248,7 +253,7 @@ void emu_set_injected_draws(void* h, const uint8_t* d, int64_t len) { ((EmuEnv*)
 
 void emu_reset(void* h, const uint8_t* reset_mask, const int8_t* init_boards) {
     EmuEnv* e = (EmuEnv*)h;
-    g_params = e->p; g_params.reset_mask = reset_mask; g_params.init_boards = init_boards; g_params.pool_tag = e->tag;
+    g_params = e->p; g_params.reset_mask = reset_mask; g_params.init_boards = init_boards; g_params.pool_tag = e->tag; g_params.commit_pregen = 1;
     DISPATCH(e_reset)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
         g_params = e->p; g_params.pool_tag = e->tag++;
@@ -257,10 +262,12 @@ void emu_reset(void* h, const uint8_t* reset_mask, const int8_t* init_boards) {
 }
 void emu_step(void* h, const int32_t* actions) {
     EmuEnv* e = (EmuEnv*)h;
-    g_params = e->p; g_params.actions = actions; g_params.pool_tag = e->tag; g_params.seq = e->seq++ & 1;
+    const bool close_batch = ++e->since_pregen >= e->pregen_every;
+    g_params = e->p; g_params.actions = actions; g_params.pool_tag = e->tag; g_params.seq = e->seq++ & 1; g_params.commit_pregen = close_batch;
     launch_threads(e_gate, e->p.N, GATE_EPT);
     DISPATCH(e_step)
-    if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
+    if (close_batch) e->since_pregen = 0;
+    if (close_batch && !e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
         g_params = e->p; g_params.pool_tag = e->tag++;
         DISPATCH(e_pregen)
     }
@@ -269,7 +276,7 @@ void emu_step_many(void* h, const int32_t* actions, int T, int32_t* rewards, uin
     EmuEnv* e = (EmuEnv*)h;
     g_params = e->p; g_params.actions = actions; g_params.T = T; g_params.ro_reward = rewards; g_params.ro_terminated = terminated;
     g_params.policy = policy; g_params.ro_actions = actions_out;
-    g_params.pool_tag = e->tag;
+    g_params.pool_tag = e->tag; g_params.commit_pregen = 1;
     DISPATCH(e_rollout)
     if (!e->p.use_inj && !(e->p.flags & 2u) && e->p.autoreset != 0) {
         g_params = e->p; g_params.pool_tag = e->tag++;
@@ -284,6 +291,11 @@ void emu_legal_mask(void* h) {
 void emu_debug_op(void* h, int op, const int32_t* args) {
     EmuEnv* e = (EmuEnv*)h;
     g_params = e->p; g_params.dbg_op = op; g_params.dbg_args = args;
+    DISPATCH(e_debug)
+}
+void emu_debug_lines(void* h, uint32_t* out, int byte_planes) {
+    EmuEnv* e = (EmuEnv*)h;
+    g_params = e->p; g_params.dbg_op = OP_LINES | (byte_planes ? OP_BYTE_PLANES : 0); g_params.dbg_args = nullptr; g_params.dbg_out = out;
     DISPATCH(e_debug)
 }
 }

@@ -25,6 +25,7 @@
 
 struct uint2 { uint32_t x, y; };
 struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { uint2 v; v.x = x; v.y = y; return v; }
 
 namespace emu {
 struct Dim { unsigned x, y, z; };

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("TMG_B200_LIB", os.path.join(_HERE, "libtmg_b200.so"))  # override: A/B builds only
 SRC = os.path.join(_HERE, "csrc", "tmg_b200.cu")
 DEVICE_HDR = os.path.join(_HERE, "csrc", "tmg_device.cuh")
+RB_HDR = os.path.join(_HERE, "csrc", "tmg_rb.cuh")
 ABI_HDR = os.path.join(ROOT, "include", "tmg_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -24,6 +25,9 @@ REFILL = {"philox": 0, "injected": 1}
 POLICY = {"uniform": 1, "mask": 2}
 FLAG_NO_MASK = 1
 FLAG_NO_PREGEN = 2
+FLAG_BYTE_PLANES = 4
+OP_BYTE_PLANES = 0x100
+LINES_WORDS = 65
 
 ST_BAD_ACTION, ST_NEEDS_RESET, ST_DRAWS_EXHAUSTED, ST_RESET_CAP = 1, 2, 4, 8
 ST_LINE_OVERFLOW, ST_DFS_OVERFLOW, ST_INVALID_BOARD, ST_INTERNAL = 16, 32, 64, 128
@@ -59,6 +63,7 @@ class HostIO(C.Structure):
 
 EXPORTS = {
     "tmg_abi_version": (C.c_int, []),
+    "tmg_build_id": (C.c_char_p, []),
     "tmg_error_string": (C.c_char_p, [C.c_int]),
     "tmg_status_string": (C.c_char_p, [C.c_uint32]),
     "tmg_num_actions": (C.c_int, [C.c_int32, C.c_int32]),
@@ -82,19 +87,47 @@ EXPORTS = {
     "tmg_host_bind": (C.c_int, [C.c_void_p, C.POINTER(HostIO), C.c_void_p]),
     "tmg_set_profile_buffer": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_debug_op": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tmg_debug_lines": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 
+def source_build_id() -> str:
+    """sha256 over the CUDA sources, the ABI header and the compiler flags: what the library must have been built from."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in (SRC, DEVICE_HDR, RB_HDR, ABI_HDR):
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:32]
+
+
+def built_build_id(path: str = None) -> str:
+    """The build id embedded in a built library (read from the file, the library is not loaded)."""
+    path = path or LIB_PATH
+    try:
+        with open(path, "rb") as f:
+            blob = f.read()
+    except OSError:
+        return ""
+    i = blob.find(b"TMG_BUILD_ID=")
+    return blob[i + 13:i + 45].decode("ascii", "replace") if i >= 0 else ""
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    deps = [SRC, DEVICE_HDR, ABI_HDR]
-    stale = not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(d) for d in deps)
-    if force or stale:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU).  The library embeds a hash of
+    the sources it was built from; it is rebuilt whenever that differs from the sources in the tree (not mtime-gated)."""
+    want = source_build_id()
+    if force or built_build_id() != want:
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-        cmd = [nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", LIB_PATH, SRC]
+        tmp = LIB_PATH + ".tmp"
+        cmd = [nvcc] + NVCC_FLAGS + [f"-DTMG_BUILD_ID_STR=\"{want}\"", "-I", os.path.join(ROOT, "include"), "-o", tmp, SRC]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)
+        os.replace(tmp, LIB_PATH)
+        if built_build_id() != want:
+            raise RuntimeError("libtmg_b200.so does not carry the build id of its sources")
     return LIB_PATH
 
 

@@ -21,14 +21,19 @@ struct tmg_env {
     uint8_t* mask_bits_dev;
     void* base;     // one allocation backs every buffer
     size_t bytes;
-    // board pool: k_pregen runs on a side stream so that generate_board stays off the step path
-    static constexpr int SIDE = 4;    // independent refill launches overlap each other and the steps
-    static constexpr int RING = tmg::PG_RING;   // multiple of SIDE: an event slot always belongs to the same side stream
-    cudaStream_t side[SIDE];
+    // board pool: k_pregen runs on ONE side stream (refills are served strictly in request order, so the pool entry of an
+    // env is only ever written by one launch at a time), off the step path.  Requests name their board ({env, board
+    // number}), and a consumer takes an entry only if its number matches, so correctness never depends on when a refill
+    // runs; the waits below only keep refills ahead of the steps that will want them and bound the launches in flight.
+    static constexpr int RING = tmg::PG_RING;
+    cudaStream_t side;
     cudaEvent_t ev_step, ev_pregen[RING];
-    long long pregen_count;   // number of k_pregen launches so far
-    cudaStream_t waited_stream;           // the caller stream of the last wait_pregen ...
-    long long waited_tag[SIDE];           // ... and the latest tag of each side stream it has waited for
+    long long pregen_count;          // number of k_pregen launches so far (= tag of the next one)
+    long long pregen_step[RING];     // step_count when launch `tag` was issued, at tag % RING
+    long long waited_upto;           // every launch with tag <= this has been waited for by waited_stream
+    cudaStream_t waited_stream;
+    int pregen_every;                // a k_pregen launch serves the requests of this many tmg_step calls
+    int steps_since_pregen;
     long long step_count;     // number of tmg_step calls so far (parity selects the work-list counters)
     int persistent_blocks;    // resident-block slots of the device for k_work / k_pregen (persistent groups)
     int pregen_grid_cap;      // diagnostics: cap on the blocks of a k_pregen launch
@@ -70,20 +75,27 @@ template <typename F> int launch_by_shape(const tmg_env* e, F&& f) {
         if (R == 9 && C == 9) return f(Shape<32, 9, 9>());
         if (R == 32 && C == 32) return f(Shape<32, 32, 32>());
     }
+#ifdef TMG_SUBWARP_GROUPS   // 2-4 boards per warp: measured slower on B200 at every batch size, kept for experiments only
     switch (e->L) {
         case 8: return f(Shape<8, 0, 0>());
         case 10: return f(Shape<10, 0, 0>());
         case 16: return f(Shape<16, 0, 0>());
-        default: return f(Shape<32, 0, 0>());
+        default: break;
     }
+#endif
+    return f(Shape<32, 0, 0>());
 }
 template <typename F> int launch_by_lanes(const tmg_env* e, F&& f) {
+#ifdef TMG_SUBWARP_GROUPS
     switch (e->L) {
         case 8: return f(std::integral_constant<int, 8>());
         case 10: return f(std::integral_constant<int, 10>());
         case 16: return f(std::integral_constant<int, 16>());
-        default: return f(std::integral_constant<int, 32>());
+        default: break;
     }
+#endif
+    (void)e;
+    return f(std::integral_constant<int, 32>());
 }
 
 int last_error() { return cudaGetLastError() == cudaSuccess ? TMG_OK : TMG_ERR_CUDA; }
@@ -92,32 +104,41 @@ template <int L> int grid_for(int n) { return (n + Cfg<L>::GPB - 1) / Cfg<L>::GP
 
 }  // namespace
 
-// `st` waits until every k_pregen launch with tag <= upto has finished: one wait per side stream, and only for
-// streams whose latest such launch this stream has not waited for already (a step usually adds one new tag)
+// `st` waits until every k_pregen launch with tag <= upto has finished (one in-order side stream: one event is enough)
 static bool wait_pregen(tmg_env* e, cudaStream_t st, long long upto) {
     if (!e->pregen) return true;
-    if (st != e->waited_stream) {           // another caller stream: it has waited for nothing yet
-        e->waited_stream = st;
-        for (int s = 0; s < tmg_env::SIDE; ++s) e->waited_tag[s] = -1;
-    }
-    for (int s = 0; s < tmg_env::SIDE; ++s) {
-        if (upto < s) continue;
-        const long long j = upto - ((upto - s) % tmg_env::SIDE);   // latest tag <= upto on side stream s
-        if (j <= e->waited_tag[s]) continue;
-        // (if that slot was reused by a later launch of the same stream the wait is only stronger)
-        if (cudaStreamWaitEvent(st, e->ev_pregen[j % tmg_env::RING], 0) != cudaSuccess) return false;
-        e->waited_tag[s] = j;
-    }
+    if (upto >= e->pregen_count) upto = e->pregen_count - 1;
+    if (st != e->waited_stream) { e->waited_stream = st; e->waited_upto = -1; }   // another caller stream has waited for nothing yet
+    if (upto <= e->waited_upto) return true;
+    if (e->pregen_count - upto < tmg_env::RING) {    // (an older slot was reused by a later launch: waiting for that one is stronger)
+        if (cudaStreamWaitEvent(st, e->ev_pregen[upto % tmg_env::RING], 0) != cudaSuccess) return false;
+    } else if (cudaStreamWaitEvent(st, e->ev_pregen[(e->pregen_count - 1) % tmg_env::RING], 0) != cudaSuccess) return false;
+    e->waited_upto = upto;
     return true;
 }
 static bool join_pregen(tmg_env* e, cudaStream_t st) { return wait_pregen(e, st, e->pregen_count - 1); }
-// after a kernel on `st` that tagged pool requests with e->pregen_count: serve them on a side stream
+// Before a kernel on `st` that may consume pool entries: wait for the refills whose boards can be due by now (their
+// requests are at least num_moves - pregen_every steps old) and keep at most 3 launches in flight.
+static bool wait_due_pregen(tmg_env* e, cudaStream_t st) {
+    if (!e->pregen) return true;
+    long long upto = e->pregen_count - 4;
+    const long long slack = e->p.num_moves - e->pregen_every;
+    for (long long j = e->pregen_count - 1; j > upto && j >= 0; --j)
+        if (e->step_count - e->pregen_step[j % tmg_env::RING] >= slack) { upto = j; break; }
+    return upto < 0 || wait_pregen(e, st, upto);
+}
+// Does the launch about to be issued on the step stream close a batch of pool requests (so that k_pregen follows it)?
+static bool closes_batch(tmg_env* e, bool is_step) {
+    if (!e->pregen) return false;
+    if (!is_step) return true;
+    return e->steps_since_pregen + 1 >= e->pregen_every;
+}
+// after a kernel on `st` that closed the batch tagged e->pregen_count: serve it on the side stream
 static int launch_pregen(tmg_env* e, cudaStream_t st) {
     if (!e->pregen) return TMG_OK;
     const long long tag = e->pregen_count;
-    cudaStream_t side = e->side[tag % tmg_env::SIDE];
     if (cudaEventRecord(e->ev_step, st) != cudaSuccess) return TMG_ERR_CUDA;
-    if (cudaStreamWaitEvent(side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
+    if (cudaStreamWaitEvent(e->side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
     Params p = e->p;
     p.pool_tag = (int)(tag & 0x7fffffff);
     const int rc = launch_by_shape(e, [&](auto shape) {
@@ -126,18 +147,29 @@ static int launch_pregen(tmg_env* e, cudaStream_t st) {
         int grid = grid_for<L>(p.N);
         if (grid > e->persistent_blocks) grid = e->persistent_blocks;
         if (grid > e->pregen_grid_cap) grid = e->pregen_grid_cap;
-        k_pregen<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), side>>>(p);
+        k_pregen<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), e->side>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
-    if (cudaEventRecord(e->ev_pregen[tag % tmg_env::RING], side) != cudaSuccess) return TMG_ERR_CUDA;
+    if (cudaEventRecord(e->ev_pregen[tag % tmg_env::RING], e->side) != cudaSuccess) return TMG_ERR_CUDA;
+    e->pregen_step[tag % tmg_env::RING] = e->step_count;
     ++e->pregen_count;
+    e->steps_since_pregen = 0;
     return TMG_OK;
 }
 
 extern "C" {
 
 int tmg_abi_version(void) { return TMG_ABI_VERSION; }
+
+#ifndef TMG_BUILD_ID_STR
+#define TMG_BUILD_ID_STR "unidentified-build"
+#endif
+// hash of the sources this library was compiled from (tile_match_gym_b200/_native.py compares it with the tree)
+const char* tmg_build_id(void) {
+    static const char id[] = "TMG_BUILD_ID=" TMG_BUILD_ID_STR;
+    return id + 13;
+}
 
 const char* tmg_error_string(int code) {
     switch (code) {
@@ -202,13 +234,15 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     // Sub-warp groups (2-4 boards per warp) are supported by the same code and were the first design, but measured
     // slower on B200 at every batch size up to 262 144 envs (65 536 envs: 232 M vs 253 M steps/s; 1 024 envs: 8.6 M vs
     // 11.5 M): the groups of a warp diverge into separate instruction streams anyway, their collectives need a
-    // runtime membership check, and the step is bound by instruction supply, not by lanes.  TMG_B200_LANES=8|10|16
-    // selects them (runtime-shape kernels) for experiments.
+    // runtime membership check, and the step is bound by instruction supply, not by lanes.  A build with
+    // -DTMG_SUBWARP_GROUPS instantiates them (TMG_B200_LANES=8|10|16 then selects one); the product build does not.
     e->L = 32;
+#ifdef TMG_SUBWARP_GROUPS
     if (const char* lanes = getenv("TMG_B200_LANES")) {
         const int l = atoi(lanes);
         if ((l == 8 && C <= 8 && R <= 16) || (l == 10 && C <= 10 && R <= 16) || (l == 16 && C <= 16 && R <= 16)) e->L = l;
     }
+#endif
     e->planes = tmg_onehot_planes(K, cfg->specials);
     Params& p = e->p;
     memset(&p, 0, sizeof(p));
@@ -238,9 +272,9 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_pool_status = take((size_t)N * 4), o_mask_bits = take((size_t)N * ((p.A + 7) / 8)),
                  o_ctl = take((size_t)CTL_WORDS * 4), o_items = take((size_t)N * sizeof(uint2)),
                  o_nsp = take((size_t)N);
-    size_t req_cap = 1;
-    while (req_cap < (size_t)N) req_cap <<= 1;
-    const size_t o_ring = take(req_cap * 4);
+    size_t req_cap = 1;   // requests of the launches in flight plus the batch being collected; an overwritten entry is harmless
+    while (req_cap < (size_t)8 * N) req_cap <<= 1;
+    const size_t o_ring = take(req_cap * sizeof(uint2));
     e->bytes = off;
     if (cudaMalloc(&e->base, e->bytes) != cudaSuccess) { cudaGetLastError(); delete e; return TMG_ERR_OOM; }
     if (cudaMemset(e->base, 0, e->bytes) != cudaSuccess) { cudaFree(e->base); delete e; return TMG_ERR_CUDA; }
@@ -272,11 +306,17 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
     e->waited_stream = nullptr;
-    for (int i = 0; i < tmg_env::SIDE; ++i) e->waited_tag[i] = -1;
+    e->waited_upto = -1;
     e->step_count = 0;
+    e->steps_since_pregen = 0;
+    // One k_pregen launch per `pregen_every` steps: a board requested at an episode end is wanted num_moves steps later,
+    // so the requests of a few steps are served together (fewer, fuller launches when the episode phases differ).
+    e->pregen_every = cfg->num_moves >= 8 ? (cfg->num_moves / 4 < 8 ? cfg->num_moves / 4 : 8) : 1;
+    if (const char* pe = getenv("TMG_B200_PREGEN_EVERY")) { if (atoi(pe) > 0) e->pregen_every = atoi(pe); }
+    for (int i = 0; i < tmg_env::RING; ++i) e->pregen_step[i] = 0;
     e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr; e->hm_terminated = nullptr;
     e->hm_reward = nullptr; e->hm_moves_left = nullptr; e->hm_bound = false;
-    p.req_ring = e->pregen ? reinterpret_cast<int32_t*>(b + o_ring) : nullptr;
+    p.req_ring = e->pregen ? reinterpret_cast<uint2*>(b + o_ring) : nullptr;
     e->persistent_blocks = prop.multiProcessorCount * TMG_STEP_MIN_BLOCKS;
     {
         const char* ppsm = getenv("TMG_B200_BLOCKS_PER_SM");   // tuning knob: persistent blocks per SM
@@ -289,11 +329,11 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
         const int per_sm = capenv ? atoi(capenv) : 0;
         e->pregen_grid_cap = per_sm > 0 ? prop.multiProcessorCount * per_sm : 0x7fffffff;
     }
-    for (int i = 0; i < tmg_env::SIDE; ++i) e->side[i] = nullptr;
+    e->side = nullptr;
     bool ok = cudaMemset(p.episode, 0xff, (size_t)N * 4) == cudaSuccess &&       // -1: no board generated yet
               cudaMemset(p.pool_episode, 0x80, (size_t)N * 4) == cudaSuccess;    // never equal to a real episode
     if (e->pregen) {
-        for (int i = 0; i < tmg_env::SIDE; ++i) ok = ok && cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming) == cudaSuccess;
         for (int i = 0; i < tmg_env::RING; ++i) ok = ok && cudaEventCreateWithFlags(&e->ev_pregen[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -309,10 +349,10 @@ int tmg_destroy(tmg_env* e) {
     if (!e) return TMG_ERR_INVALID_ARG;
     cudaSetDevice(e->cfg.device);
     if (e->pregen) {
-        for (int i = 0; i < tmg_env::SIDE; ++i) cudaStreamSynchronize(e->side[i]);
+        cudaStreamSynchronize(e->side);
         cudaEventDestroy(e->ev_step);
         for (int i = 0; i < tmg_env::RING; ++i) cudaEventDestroy(e->ev_pregen[i]);
-        for (int i = 0; i < tmg_env::SIDE; ++i) cudaStreamDestroy(e->side[i]);
+        cudaStreamDestroy(e->side);
     }
     cudaFree(e->base);
     delete e;
@@ -393,6 +433,7 @@ int tmg_reset(tmg_env* e, const uint8_t* reset_mask_dev, const int8_t* init_boar
     p.init_boards = init_boards_dev;
     p.init_vecw = init_boards_dev ? ptr_vec_width(init_boards_dev, p.board_vecw) : p.board_vecw;
     p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
+    p.commit_pregen = closes_batch(e, false);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!join_pregen(e, st)) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
@@ -415,12 +456,9 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
     p.seq = (int)(e->step_count++ & 1);
-    if (e->pregen) {
-        // An env consumes its pool entry at most once per episode, so only refills tagged num_moves or more launches
-        // ago can be needed by this step; everything newer keeps running beside the step kernels.
-        const long long W = p.num_moves < 24 ? p.num_moves : 24;   // < RING - SIDE so the event slots are still live
-        if (!wait_pregen(e, st, e->pregen_count - W)) return TMG_ERR_CUDA;
-    }
+    const bool close_batch = closes_batch(e, true);
+    p.commit_pregen = close_batch;
+    if (!wait_due_pregen(e, st)) return TMG_ERR_CUDA;
     k_gate<<<(p.N + 128 * GATE_EPT - 1) / (128 * GATE_EPT), 128, 0, st>>>(p);
     if (last_error() != TMG_OK) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
@@ -428,11 +466,18 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
         constexpr int L = S::L;
         int grid = grid_for<L>(p.N);
         if (grid > e->persistent_blocks) grid = e->persistent_blocks;
-        k_work<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        if constexpr (UsesRB<L, S::R>::maybe) {   // the register-resident engine where it applies (tmg_rb.cuh)
+            if (rb_supported(L, p.R, p.K, p.flags)) {
+                k_work<L, S::R, S::C, true><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+                return last_error();
+            }
+        }
+        k_work<L, S::R, S::C, false><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
-    return launch_pregen(e, st);
+    ++e->steps_since_pregen;
+    return close_batch ? launch_pregen(e, st) : TMG_OK;
 }
 
 static int rollout(tmg_env* e, int policy, const int32_t* actions_dev, int32_t num_steps, int32_t* actions_out_dev,
@@ -448,17 +493,24 @@ static int rollout(tmg_env* e, int policy, const int32_t* actions_dev, int32_t n
     p.ro_reward = rewards_dev;
     p.ro_terminated = terminated_dev;
     p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
+    p.commit_pregen = closes_batch(e, false);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // No wait for the recent pool refills: k_rollout takes a pool entry only if its episode number says it is complete
-    // (published last by k_pregen) and generates the board itself otherwise -- the same bytes either way.  Refills of
-    // 24 or more launches ago are waited for, so that their range / event slots (rings of PG_RING) can be reused.
-    if (e->pregen && !wait_pregen(e, st, e->pregen_count - 24)) return TMG_ERR_CUDA;
+    // No wait for the recent pool refills: k_rollout takes a pool entry only if its board number says it is the one it
+    // wants and complete (published last by k_pregen) and generates the board itself otherwise -- the same bytes either
+    // way.  Only the number of refill launches in flight is bounded (range / event slots are rings of PG_RING).
+    if (e->pregen && !wait_pregen(e, st, e->pregen_count - 4)) return TMG_ERR_CUDA;
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
         int grid = grid_for<L>(p.N);
         if (grid > e->persistent_blocks) grid = e->persistent_blocks;
-        k_rollout<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        if constexpr (UsesRB<L, S::R>::maybe) {   // the register-resident engine where it applies (tmg_rb.cuh)
+            if (rb_supported(L, p.R, p.K, p.flags)) {
+                k_rollout<L, S::R, S::C, true><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+                return last_error();
+            }
+        }
+        k_rollout<L, S::R, S::C, false><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;
@@ -516,7 +568,17 @@ int tmg_clear_status(tmg_env* e, void* stream) {
 
 int tmg_join(tmg_env* e, void* stream) {
     if (!e) return TMG_ERR_INVALID_ARG;
-    return join_pregen(e, static_cast<cudaStream_t>(stream)) ? TMG_OK : TMG_ERR_CUDA;
+    if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (e->pregen && e->steps_since_pregen > 0) {   // requests collected since the last launch: serve them now
+        Params p = e->p;
+        p.pool_tag = (int)(e->pregen_count & 0x7fffffff);
+        k_commit_batch<<<1, 1, 0, st>>>(p);
+        if (last_error() != TMG_OK) return TMG_ERR_CUDA;
+        const int rc = launch_pregen(e, st);
+        if (rc != TMG_OK) return rc;
+    }
+    return join_pregen(e, st) ? TMG_OK : TMG_ERR_CUDA;
 }
 
 int tmg_set_seed(tmg_env* e, uint64_t seed, void* stream) {
@@ -585,12 +647,14 @@ int tmg_set_profile_buffer(tmg_env* e, uint32_t* prof_dev) {
     return TMG_OK;
 }
 
-int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) {
-    if (!e || op < TMG_OP_GRAVITY || op > TMG_OP_COUNT_LINES) return TMG_ERR_INVALID_ARG;
+static int debug_launch(tmg_env* e, int32_t op, const int32_t* args_dev, uint32_t* out_dev, void* stream) {
+    const int base = op & 0xff;
+    if (!e || base < TMG_OP_GRAVITY || base > TMG_OP_LINES || (op & ~(0xff | TMG_OP_BYTE_PLANES))) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     Params p = e->p;
     p.dbg_op = op;
     p.dbg_args = args_dev;
+    p.dbg_out = out_dev;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!join_pregen(e, st)) return TMG_ERR_CUDA;
     const int rc = launch_by_lanes(e, [&](auto lanes) {
@@ -599,6 +663,16 @@ int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) 
         return last_error();
     });
     return rc != TMG_OK ? rc : refresh_mirror(e, st);
+}
+
+int tmg_debug_op(tmg_env* e, int32_t op, const int32_t* args_dev, void* stream) {
+    if ((op & 0xff) == TMG_OP_LINES) return TMG_ERR_INVALID_ARG;   // needs an output buffer: tmg_debug_lines
+    return debug_launch(e, op, args_dev, nullptr, stream);
+}
+
+int tmg_debug_lines(tmg_env* e, uint32_t* out_dev, int32_t byte_planes, void* stream) {
+    if (!out_dev) return TMG_ERR_INVALID_ARG;
+    return debug_launch(e, TMG_OP_LINES | (byte_planes ? TMG_OP_BYTE_PLANES : 0), nullptr, out_dev, stream);
 }
 
 }  // extern "C"

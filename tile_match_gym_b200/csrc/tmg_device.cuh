@@ -58,9 +58,10 @@ enum : uint32_t {
 };
 enum : uint32_t { SP_COOKIE = 1u, SP_VLASER = 2u, SP_HLASER = 4u, SP_BOMB = 8u };
 enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 };
-enum : uint32_t { FLAG_NO_MASK = 1u, FLAG_NO_PREGEN = 2u };
+enum : uint32_t { FLAG_NO_MASK = 1u, FLAG_NO_PREGEN = 2u, FLAG_BYTE_PLANES = 4u };
 enum { OP_GRAVITY = 1, OP_REFILL, OP_RESOLVE_ROUND, OP_ACTIVATE, OP_COMBINE, OP_MOVE, OP_EFFECTIVE, OP_GENERATE,
-       OP_SHUFFLE, OP_COUNT_LINES };
+       OP_SHUFFLE, OP_COUNT_LINES, OP_LINES, OP_LAST = OP_LINES, OP_BYTE_PLANES = 0x100 };
+enum { LINES_WORDS = 1 + 2 * 32 };   // OP_LINES output per env: n, then {info, cell set} per line (see RBoard::line_info)
 enum { POLICY_GIVEN = 0, POLICY_UNIFORM = 1, POLICY_MASK = 2 };
 enum { NAME_NORMAL = 0, NAME_VLASER = 2, NAME_HLASER = 3, NAME_BOMB = 4, NAME_COOKIE = -1 };  // = created tile type
 
@@ -99,8 +100,10 @@ struct Params {
     uint32_t* ctl;           // control words
     uint2* wl_items;         // [N] work list of the current step: {env, action | flags << 12}; high priority from the front, rest from the back
     uint8_t* n_special;      // [N] special tiles on the env's board (scheduling hint only: a stale value costs time, never correctness)
-    int32_t* req_ring;       // [req_mask + 1] envs whose pool entry must be refilled, in request order (NULL: pool not in use)
-    uint32_t req_mask;       // ring capacity - 1 (capacity = power of two >= N)
+    uint2* req_ring;         // [req_mask + 1] pool-refill requests {env, board number}, in request order (NULL: pool not in use).
+                             // A request names the board it wants, so a late, repeated or overwritten entry is harmless.
+    uint32_t req_mask;       // ring capacity - 1 (capacity = power of two >= 8 N)
+    int commit_pregen;       // this launch closes a batch of requests: the next k_pregen launch serves [CTL_REQ_PREV, tail)
     int seq;                 // number of this tmg_step call: its parity selects the work-list counters
     // host mirror (tmg_host_bind): page-locked host arrays, as device-visible pointers, that the step kernel updates in
     // place over PCIe for exactly the envs whose board / mask changed (NULL = not bound)
@@ -121,6 +124,7 @@ struct Params {
     int policy;              // 0: actions given; POLICY_UNIFORM / POLICY_MASK: drawn inside the kernel from stream 2
     const int32_t* dbg_args;
     int dbg_op;
+    uint32_t* dbg_out;       // OP_LINES: [N][LINES_WORDS]
     uint32_t* prof;  // optional [N][8]: cycles total, cycles in the general path, cascade rounds, redraw iterations,
                      // then general-path cycles split into scan / line table / classification / resolution (zero before each step)
 };
@@ -1751,6 +1755,37 @@ __device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params*
     return o;
 }
 
+#include "tmg_rb.cuh"
+
+// Which engine runs the moves of a step kernel instantiation: the register-resident one (tmg_rb.cuh) for boards of up to
+// 10 rows and 7 colours, the byte planes in shared memory otherwise (or when TMG_FLAG_BYTE_PLANES asks for them).
+// The step kernels take the choice as a template argument (RBK), made by the host with rb_supported(): an instantiation
+// carries the move code of one engine only.
+template <int L, int RT> struct UsesRB { static constexpr bool maybe = L == 32 && RT <= 10; };
+__host__ __device__ inline bool rb_supported(int lanes, int R, int K, uint32_t flags) {
+    return lanes == 32 && R <= 10 && K <= 7 && !(flags & FLAG_BYTE_PLANES);
+}
+// A move on the register-resident engine for a Board whose byte planes are staged in shared memory: pack, move, mask,
+// unpack.  Returns the eliminations (without num_new_specials); mask_ok <- effv / effh are the mask of the final board
+// and a move is possible (otherwise the caller runs Board::playability on the byte planes: shuffle / literal rule).
+template <int RT, int CT, typename B>
+__device__ __forceinline__ int rb_move(RBoard<RT, CT>& rb, B& b, int i1, int i2, int& is_comb, unsigned& effv, unsigned& effh, bool& mask_ok) {
+    rb.dcur = b.dcur;
+    rb.status = 0u;
+    rb.pack_from_smem();
+    const int elim = rb.move(i1, i2, is_comb);
+    bool literal = false;
+    const bool any = rb.mask_bits(effv, effh, literal);
+    mask_ok = any && !literal;
+    b.sync();
+    rb.unpack_to_smem();
+    b.sync();
+    b.dcur = rb.dcur; b.n_new = rb.n_new; b.n_act = rb.n_act; b.status |= rb.status;
+    b.last_S = rb.bits_S();
+    b.prof_rounds += rb.prof_rounds; b.prof_iters += rb.prof_general;
+    return elim;
+}
+
 // ======================================================================================================
 // kernels
 // ======================================================================================================
@@ -1805,12 +1840,14 @@ __device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers,
     __threadfence();
     if (atomicAdd(&p.ctl[CTL_DONE], 1u) != callers - 1u) return;
     __threadfence();
-    const uint32_t tail = ctl_read(&p.ctl[CTL_REQ_TAIL]), prev = p.ctl[CTL_REQ_PREV];
-    const int slot = p.pool_tag % PG_RING;
-    p.ctl[CTL_PG_RANGE + 2 * slot] = prev;
-    p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
-    p.ctl[CTL_PG_HEAD + slot] = 0u;
-    p.ctl[CTL_REQ_PREV] = tail;
+    if (p.commit_pregen) {   // the host launches k_pregen `pool_tag` after this launch: it serves the requests since the last batch
+        const uint32_t tail = ctl_read(&p.ctl[CTL_REQ_TAIL]), prev = p.ctl[CTL_REQ_PREV];
+        const int slot = p.pool_tag % PG_RING;
+        p.ctl[CTL_PG_RANGE + 2 * slot] = prev;
+        p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
+        p.ctl[CTL_PG_HEAD + slot] = 0u;
+        p.ctl[CTL_REQ_PREV] = tail;
+    }
     p.ctl[CTL_RO_HEAD] = 0u;
     if (is_step) {
         const int nq = (p.seq & 1) ^ 1;
@@ -1859,7 +1896,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             b.end_generate();
             if (gc.lane == 0) {
                 p.episode[gc.env] = ep;
-                if (p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = gc.env;   // next board -> pool
+                if (p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = make_uint2((uint32_t)gc.env, (uint32_t)(ep + 1));   // next board -> pool
             }
         }
         b.store_board();
@@ -1885,11 +1922,11 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
     const int env0 = ((int)blockIdx.x * 4 + ((int)threadIdx.x >> 5)) * (32 * GATE_EPT) + wl;   // this thread: env0 + 32 k
     const int q = p.seq & 1;
     bool heavy[GATE_EPT], hi[GATE_EPT], req[GATE_EPT];
-    uint32_t packed[GATE_EPT];
+    uint32_t packed[GATE_EPT], req_ep[GATE_EPT];
 #pragma unroll
     for (int k = 0; k < GATE_EPT; ++k) {
         const int env = env0 + 32 * k;
-        heavy[k] = false; hi[k] = false; req[k] = false; packed[k] = 0u;
+        heavy[k] = false; hi[k] = false; req[k] = false; packed[k] = 0u; req_ep[k] = 0u;
         if (env >= p.N) continue;
         int timer = p.timer[env];
         const int action = p.actions[env];
@@ -1936,7 +1973,11 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
         // The next board is a pure function of (seed, env, episode): take it from the pool k_pregen filled ahead of
         // time when it is there, generate it inside the step otherwise (same result either way).
         bool from_pool = false;
-        if (regenerate) from_pool = !p.use_inj && p.pool_episode[env] == p.episode[env] + 1;
+        if (regenerate) {
+            const int ep_now = p.episode[env];
+            from_pool = !p.use_inj && p.pool_episode[env] == ep_now + 1;
+            req_ep[k] = (uint32_t)(ep_now + 2);              // this step moves the env to board ep_now + 1: the pool needs the one after
+        }
         heavy[k] = eff || regenerate || zero_mask;
         hi[k] = eff && p.n_special[env] >= PRI_SPECIALS;
         req[k] = regenerate && p.req_ring != nullptr;
@@ -1970,7 +2011,7 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
             uint2 it; it.x = (uint32_t)(env0 + 32 * k); it.y = packed[k];
             p.wl_items[hi[k] ? hbase + (uint32_t)__popc(hm[k] & lt) : (uint32_t)p.N - 1u - (lbase + (uint32_t)__popc(lm[k] & lt))] = it;
         }
-        if (req[k]) p.req_ring[(rbase + (uint32_t)__popc(rm[k] & lt)) & p.req_mask] = env0 + 32 * k;
+        if (req[k]) p.req_ring[(rbase + (uint32_t)__popc(rm[k] & lt)) & p.req_mask] = make_uint2((uint32_t)(env0 + 32 * k), req_ep[k]);
         hbase += (uint32_t)__popc(hm[k]); lbase += (uint32_t)__popc(lm[k]); rbase += (uint32_t)__popc(rm[k]);
     }
     __syncwarp(0xffffffffu);
@@ -2001,12 +2042,13 @@ template <int L> __device__ __forceinline__ uint32_t pop_item(const GroupCtx<L>&
 
 // end of a work-list item: playability (ref board.py:381-391), the next board if the episode ended, state and outputs
 template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Board<L, RT, CT>& b, const Params& p, uint32_t packed,
-                                                                            int elim, int is_comb, long long prof_t0) {
+                                                                            int elim, int is_comb, long long prof_t0,
+                                                                            bool mask_ok = false, unsigned effv0 = 0u, unsigned effh0 = 0u) {
     const int lane = b.lane, env = b.env;
     const bool want_mask = !(p.flags & FLAG_NO_MASK);
     const bool eff = packed & IT_EFF, regenerate = packed & IT_REGEN, zero_mask = packed & IT_ZERO_MASK,
                from_pool = packed & IT_FROM_POOL;
-    unsigned effv = 0u, effh = 0u;
+    unsigned effv = effv0, effh = effh0;                                   // mask_ok: the mask of the moved board is known and has a move
     int shuffled = 0;
     const int reward = elim + b.n_new;                                     // ref :378 (counters are uniform across lanes)
     const int n_new = b.n_new, n_act = b.n_act;
@@ -2018,7 +2060,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
     for (int phase = 0; phase < 2; ++phase) {
         bool clean, all_normal;
         if (phase == 0) {
-            if (!eff) continue;
+            if (!eff || mask_ok) continue;
             clean = true; all_normal = false;
         } else {
             if (!inline_gen) continue;
@@ -2080,7 +2122,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
 // special tiles), so that the longest item of the launch runs beside the bulk instead of trailing it.
 // (A warp-level state machine that aligns the cascade rounds of the warp's groups, like k_pregen's loop, was measured
 // no faster here: collectives with a group mask make the groups of a warp separate instruction streams anyway.)
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_work(const __grid_constant__ Params p) {
+template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_work(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
     const int q = p.seq & 1;
@@ -2098,16 +2140,23 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         int elim = 0, is_comb = 0;
         b.sync();
         if (packed & (IT_EFF | IT_REGEN)) b.load_cursors();
+        bool mask_ok = false;
+        unsigned effv = 0u, effh = 0u;
         if (packed & IT_EFF) {
             b.load_board(p.board, p.board_vecw);
             int i1, i2;
             b.action_cells((int)(packed & IT_ACTION), i1, i2);
-            bool pending_fall = b.move_begin(i1, i2);
-            is_comb = pending_fall;
+            if constexpr (RBK && UsesRB<L, RT>::maybe) {
+                RBoard<RT, CT> rb(b.s, p, gc.lane, b.env);
+                elim = rb_move(rb, b, i1, i2, is_comb, effv, effh, mask_ok);
+            } else {
+                bool pending_fall = b.move_begin(i1, i2);
+                is_comb = pending_fall;
 #pragma unroll 1
-            while (b.cascade_trip(pending_fall, elim)) {}
+                while (b.cascade_trip(pending_fall, elim)) {}
+            }
         }
-        finish_item<L, RT, CT>(b, p, packed, elim, is_comb, prof_t0);
+        finish_item<L, RT, CT>(b, p, packed, elim, is_comb, prof_t0, mask_ok, effv, effh);
     }
 }
 
@@ -2116,7 +2165,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 // legal-move mask as bitboards in registers across the steps, so a step that changes nothing is a bit test, and no
 // env ever waits for the slowest cascade of the batch.  State and outputs after the call are those of T tmg_step
 // calls; per-step rewards / terminations go to [T][N] arrays.
-template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_rollout(const __grid_constant__ Params p) {
+template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_rollout(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
     const int lane = gc.lane;
@@ -2195,8 +2244,15 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
                 if (eff) {
                     int i1, i2;
                     b.action_cells(action, i1, i2);
-                    b.move_core(i1, i2, reward, is_comb);
-                    shuffled = b.playability(true, false, effv, effh);             // ref board.py:381-391
+                    bool mask_ok = false;
+                    if constexpr (RBK && UsesRB<L, RT>::maybe) {
+                        RBoard<RT, CT> rb(b.s, p, lane, env);
+                        reward = rb_move(rb, b, i1, i2, is_comb, effv, effh, mask_ok);
+                        reward += b.n_new;                                         // ref board.py:378
+                    } else {
+                        b.move_core(i1, i2, reward, is_comb);
+                    }
+                    if (!mask_ok) shuffled = b.playability(true, false, effv, effh);   // ref board.py:381-391
                     n_new = b.n_new; n_act = b.n_act;
                     touched = true;
                 }
@@ -2247,7 +2303,8 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         }
         if (lane == 0) {
             p.episode[env] = episode;
-            if (regenerated && p.req_ring) p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = env;   // next board -> pool
+            if (regenerated && p.req_ring)    // next board -> pool
+                p.req_ring[atomicAdd(&p.ctl[CTL_REQ_TAIL], 1u) & p.req_mask] = make_uint2((uint32_t)env, (uint32_t)(episode + 1));
         }
         write_step_outputs<L>(p, env, lane, timer, reward, terminated, is_comb, n_new, n_act, shuffled, timer >= 0);
         if (lane == 0) {
@@ -2282,9 +2339,12 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
             const uint32_t idx = pop_item<L>(gc, &p.ctl[CTL_PG_HEAD + slot]);
             if (idx >= n) done = true;
             else {
-                const int env = p.req_ring[(start + idx) & p.req_mask];
-                ep = p.episode[env] + 1;
-                if (p.pool_episode[env] != ep) {
+                // The request names its board (issued as {env, board number}), so the result does not depend on when this
+                // launch runs relative to the steps; a request the env has already moved past is skipped.
+                const uint2 rq = p.req_ring[(start + idx) & p.req_mask];
+                const int env = (int)rq.x;
+                ep = (int)rq.y;
+                if ((uint32_t)env < (uint32_t)p.N && p.pool_episode[env] != ep && p.episode[env] < ep) {
                     b.rebind(env);
                     b.sync();
                     capped = false; from = b.R - 1; iters = 0; have = true;
@@ -2355,7 +2415,74 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
     int result = 0;
     const int C = p.C;
     b.sync();
-    switch (p.dbg_op) {
+    const int op = p.dbg_op & 0xff;
+    // The primitives of the register-resident engine (tmg_rb.cuh) are exercised through the same entry point: boards it
+    // supports run on it unless OP_BYTE_PLANES asks for the byte-plane implementation.
+    if constexpr (L == 32) {
+        const bool rb_op = op == OP_GRAVITY || op == OP_RESOLVE_ROUND || op == OP_ACTIVATE || op == OP_COMBINE || op == OP_MOVE ||
+                           op == OP_COUNT_LINES || op == OP_LINES;
+        if (rb_op && !(p.dbg_op & OP_BYTE_PLANES) && rb_supported(32, p.R, p.K, p.flags)) {
+            RBoard<0, 0> rb(b.s, p, lane, env);
+            rb.dcur = b.dcur;
+            rb.n_new = b.n_new; rb.n_act = b.n_act;
+            rb.pack_from_smem();
+            int is_comb = 0, shuffled = 0;
+            bool to_bytes = true, fallback = false;
+            unsigned effv = 0u, effh = 0u;
+            switch (op) {
+                case OP_GRAVITY:
+                    result = rb.radd(__popc(rb.bits_tz() & (lane < C ? 0xffffffffu : 0u)));
+                    rb.gravity_column();
+                    break;
+                case OP_RESOLVE_ROUND: rb.literal_rounds = true; result = rb.resolve_round(); break;
+                case OP_ACTIVATE: rb.activate(a0 * C + a1, a2, a3 == 0); break;
+                case OP_COMBINE: rb.combination(a0 * C + a1, a2 * C + a3); break;
+                case OP_MOVE: {
+                    const int i1 = a0 * C + a1, i2 = a2 * C + a3;
+                    bool eff = false;
+                    if (lane == 0) eff = effective_literal(b.col, b.typ, p.R, C, i1, i2);
+                    eff = b.shfl((int)eff, 0) != 0;
+                    rb.n_new = 0; rb.n_act = 0;
+                    if (eff) {
+                        result = rb.move(min(i1, i2), max(i1, i2), is_comb);
+                        result += rb.n_new;
+                        bool literal = false;
+                        fallback = !rb.mask_bits(effv, effh, literal) || literal;
+                    }
+                    break;
+                }
+                default: {                                   // OP_COUNT_LINES / OP_LINES
+                    const typename RBoard<0, 0>::Scan sc = rb.scan_lines();
+                    result = sc.rstar < 0 ? 0 : rb.build_line_table(sc);
+                    to_bytes = false;
+                    if (op == OP_LINES && p.dbg_out) {
+                        uint32_t* out = p.dbg_out + (size_t)env * LINES_WORDS;
+                        if (lane == 0) out[0] = (uint32_t)result;
+                        if (lane < result) { out[1 + 2 * lane] = b.s.line_key[lane]; out[2 + 2 * lane] = b.s.line_mask[lane]; }
+                    }
+                    break;
+                }
+            }
+            if (to_bytes) {
+                b.sync();
+                rb.unpack_to_smem();
+                b.sync();
+            }
+            b.dcur = rb.dcur; b.n_new = rb.n_new; b.n_act = rb.n_act; b.status |= rb.status;
+            if (fallback) shuffled = b.playability(true, false, effv, effh);
+            if (op == OP_MOVE && lane == 0) { p.is_comb[env] = (uint8_t)is_comb; p.shuffled[env] = (uint8_t)shuffled; }
+            b.store_board();
+            b.store_cursors();
+            merge_status(b, p);
+            if (lane == 0) {
+                p.reward[env] = result;
+                p.new_specials[env] = b.n_new;
+                p.activated[env] = b.n_act;
+            }
+            return;
+        }
+    }
+    switch (op) {
         case OP_GRAVITY: b.gravity(&result); break;
         case OP_REFILL: {
             // refill() expects the post-gravity layout; a general board is handled row by row instead:
@@ -2424,9 +2551,19 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
             break;
         }
         case OP_SHUFFLE: b.shuffle(); break;
-        case OP_COUNT_LINES: {
+        case OP_COUNT_LINES:
+        case OP_LINES: {
             const typename Board<L>::Scan sc = b.scan_lines(p.R - 1, false);
             result = sc.rstar < 0 ? 0 : b.build_line_table(sc);
+            if (op == OP_LINES && p.dbg_out) {               // the line table in the entry format of RBoard::line_info
+                uint32_t* out = p.dbg_out + (size_t)env * LINES_WORDS;
+                if (lane == 0) out[0] = (uint32_t)min(result, 32);
+                for (int i = lane; i < min(result, 32); i += L)  {
+                    out[1 + 2 * i] = (b.s.line_key[i] & 0xffffu) | ((uint32_t)b.s.line_kind[i] << 16) | ((uint32_t)b.s.line_idx[i] << 17) |
+                                     ((uint32_t)(b.s.line_colour[i] & 7u) << 22);
+                    out[2 + 2 * i] = b.s.line_mask[i];
+                }
+            }
             break;
         }
         default: break;
@@ -2494,6 +2631,16 @@ __global__ void __launch_bounds__(256) k_pack_mask(const uint8_t* __restrict__ m
     for (int j = 0; j < 8; ++j)
         if (8 * b + j < A) v |= (unsigned)(m[j] != 0) << j;
     out[i] = (uint8_t)v;
+}
+
+// closes the batch of pool requests collected so far under p.pool_tag (tmg_join: no step follows that could do it)
+__global__ void k_commit_batch(const __grid_constant__ Params p) {
+    const uint32_t tail = ctl_read(&p.ctl[CTL_REQ_TAIL]), prev = p.ctl[CTL_REQ_PREV];
+    const int slot = p.pool_tag % PG_RING;
+    p.ctl[CTL_PG_RANGE + 2 * slot] = prev;
+    p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
+    p.ctl[CTL_PG_HEAD + slot] = 0u;
+    p.ctl[CTL_REQ_PREV] = tail;
 }
 
 __global__ void k_clear_status(uint32_t* st, int n) {
