@@ -19,7 +19,25 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("TMG_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """TMG_REFERENCE_ROOT, then /root/reference (the build container), then a copy a driver may have left under
+    <repo>/baseline/_ref (git-ignored; the GPU box has none unless one was put there)."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get("TMG_REFERENCE_ROOT"), "/root/reference"]
+    base = os.path.join(here, "baseline", "_ref")
+    if os.path.isdir(base):
+        for dirpath, dirnames, filenames in os.walk(base):
+            if os.path.basename(dirpath) == "tile_match_gym" and "board.py" in filenames:
+                src = os.path.dirname(dirpath)
+                cands.append(os.path.dirname(src) if os.path.basename(src) == "src" else None)
+                break
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "tile_match_gym", "board.py")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_reference_root()
 REF_SRC = os.path.join(REF_ROOT, "src")
 
 

@@ -41,9 +41,9 @@ for t in range(a.steps):
               f"(= {cyc.max()/1.965e3:.0f} us at 1.965 GHz); sum {cyc.sum()/1e6:.0f} Mcyc")
         act = env.num_specials_activated.cpu().numpy(); new = env.num_new_specials.cpu().numpy(); rew = env.reward.cpu().numpy()
         for i in order:
-            print(f"   env {i}: cycles {cyc[i]} slow-path cycles {ser[i]} rounds {rounds[i]} redraws {iters[i]} "
-                  f"activated {act[i]} new_specials {new[i]} reward {rew[i]} | general path: scan {pr[i,4]} table {pr[i,5]} "
-                  f"classify {pr[i,6]} resolve {pr[i,7]}")
+            print(f"   env {i}: cycles {cyc[i]} general rounds (byte planes: slow-path cycles) {ser[i]} rounds {rounds[i]} redraws {iters[i]} "
+                  f"activated {act[i]} new_specials {new[i]} reward {rew[i]} | cycles: scan+fast round {pr[i,4]} general path {pr[i,5]} "
+                  f"fall+refill {pr[i,6]} (byte planes: scan / table / classify / resolve {pr[i,4]} {pr[i,5]} {pr[i,6]} {pr[i,7]})")
         eff = rounds > 0
         if eff.any():
             print(f"   effective moves {eff.sum()}: cycles/round {cyc[eff & (iters == 0)].sum() / max(1, rounds[eff & (iters == 0)].sum()):.0f}, "

@@ -1782,7 +1782,12 @@ __device__ __forceinline__ int rb_move(RBoard<RT, CT>& rb, B& b, int i1, int i2,
     b.sync();
     b.dcur = rb.dcur; b.n_new = rb.n_new; b.n_act = rb.n_act; b.status |= rb.status;
     b.last_S = rb.bits_S();
-    b.prof_rounds += rb.prof_rounds; b.prof_iters += rb.prof_general;
+    b.prof_rounds += rb.prof_rounds; b.prof_serial += rb.prof_general;   // (diagnostics: general-path rounds in the slot of the byte planes' slow-path cycles)
+    if (rb.prof_on && rb.lane == 0) {      // cycles in scan + fast round / general path / fall + refill of this move
+        atomicAdd(&rb.p.prof[rb.env * 8 + 4], rb.prof_cyc[0]);
+        atomicAdd(&rb.p.prof[rb.env * 8 + 5], rb.prof_cyc[1]);
+        atomicAdd(&rb.p.prof[rb.env * 8 + 6], rb.prof_cyc[2]);
+    }
     return elim;
 }
 
@@ -1916,7 +1921,10 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 // effectiveness gate (ref board.py:352: the maintained mask IS is_move_effective of the current board, so a no-op
 // step reads one byte and never touches its board) and the outputs of a step that changes nothing.  Envs that need
 // board work -- an effective move, a new board, a zeroed mask -- go to the work list.
-enum { GATE_EPT = 4 };   // envs per thread of k_gate: four independent chains of dependent loads per thread, a quarter of the atomics
+#ifndef TMG_GATE_EPT
+#define TMG_GATE_EPT 4
+#endif
+enum { GATE_EPT = TMG_GATE_EPT };   // envs per thread of k_gate: four independent chains of dependent loads per thread, a quarter of the atomics
 __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) {
     const int wl = (int)threadIdx.x & 31;
     const int env0 = ((int)blockIdx.x * 4 + ((int)threadIdx.x >> 5)) * (32 * GATE_EPT) + wl;   // this thread: env0 + 32 k

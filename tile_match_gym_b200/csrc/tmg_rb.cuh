@@ -24,6 +24,44 @@
 // Reference being restated (never copied): /root/reference/src/tile_match_gym/board.py, cited as "ref :NNN".
 #pragma once
 
+// The rare, large parts of a round -- the general path (line table, classification, resolution), the activation DFS and
+// the combination match -- run OUT OF LINE on the board passed and returned by value in registers, one copy each per
+// kernel, so that the common round (scan, fast path, gravity, refill) stays a small contiguous piece of code: the step
+// kernels are bound by instruction supply (the SM's instruction caches hold 6 KB / 32 KB).
+#ifndef TMG_RB_OUTLINE
+#define TMG_RB_OUTLINE 0   // measured on B200 (65 536 envs): inline 358 M steps/s, out of line 346 M
+#endif
+struct RBState { uint32_t cw, tw; int n_new, n_act; uint32_t status; int aux; };
+struct RBScanPack { int rstar; unsigned mv, hs, hcells, m; int vtop, has_v; unsigned E, D, T, S; };
+template <int RT, int CT> __device__ __noinline__ RBState rb_activate_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int cell, int t, int counted);
+template <int RT, int CT> __device__ __noinline__ RBState rb_general_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, RBScanPack sc);
+template <int RT, int CT> __device__ __noinline__ RBState rb_combination_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int i1, int i2);
+// words [4 b0, 4 b0 + 128) of stream 0 of env `gid` -> wbuf (one Philox block per lane); one copy per kernel
+#ifndef TMG_RB_FILL_NOINLINE
+#define TMG_RB_FILL_NOINLINE 1
+#endif
+#if TMG_RB_FILL_NOINLINE
+#define TMG_RB_FILL_ATTR __noinline__
+#else
+#define TMG_RB_FILL_ATTR __forceinline__
+#endif
+#ifndef TMG_RB_PROF
+#define TMG_RB_PROF 0      // per-phase cycle counters of a move (tmg_set_profile_buffer): cost 6 % even when off, so a diagnostics build only
+#endif
+#ifndef TMG_RB_SINGLE_FALL
+#define TMG_RB_SINGLE_FALL 1
+#endif
+__device__ TMG_RB_FILL_ATTR void rb_fill_words(uint32_t* wbuf, uint64_t b0, uint32_t gid, uint32_t key0, uint32_t key1, int lane) {
+    TMG_SITE_HERE
+    __syncwarp(0xffffffffu);                               // earlier reads of the buffer are done
+    const uint64_t b = b0 + (uint64_t)lane;
+    uint32_t w[4];
+    philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, 0u, key0, key1, w);
+    *reinterpret_cast<uint4*>(&wbuf[4 * lane]) = *reinterpret_cast<uint4*>(w);
+    TMG_SITE_HERE
+    __syncwarp(0xffffffffu);
+}
+
 template <int RT, int CT> struct RBoard {
     typedef Cfg<32> CF;
     static constexpr int PS = 10;                          // plane stride: rows per bit-plane
@@ -50,12 +88,16 @@ template <int RT, int CT> struct RBoard {
     bool literal_rounds = false;                           // debug entry point: a round leaves the board as the reference's resolve does
     uint32_t stk0 = 0u, stk1 = 0u;                         // DFS frames d (lane d) and 32 + d
     uint32_t prof_rounds = 0u, prof_general = 0u;
+    uint32_t prof_cyc[4] = {0u, 0u, 0u, 0u};                 // diagnostics (p.prof set): cycles in scan + fast round, general path, fall + refill, rest
+    const bool prof_on;
 
     __device__ RBoard(GroupSmem<32>& sm, const Params& pp, int lane_, int env_)
         : s(sm), p(pp), lane(lane_), env(env_), R(RT ? RT : pp.R), C(CT ? CT : pp.C), P(RT ? RT * CT : pp.P), K(pp.K),
-          gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)), specials(pp.specials) {}
+          gid((uint32_t)(pp.env_id_offset + (uint64_t)env_)), specials(pp.specials), prof_on(TMG_RB_PROF && pp.prof != nullptr) {}
 
     static __device__ __forceinline__ bool supported(const Params& pp) { return pp.R <= PS && pp.K <= 7; }
+    __device__ __forceinline__ RBState get_state() const { RBState st; st.cw = cw; st.tw = tw; st.n_new = n_new; st.n_act = n_act; st.status = status; st.aux = 0; return st; }
+    __device__ __forceinline__ void set_state(const RBState& st) { cw = st.cw; tw = st.tw; n_new = st.n_new; n_act = st.n_act; status = st.status; }
 
     // ---- warp collectives (one board per warp: literal full mask) -------------------------------------------------------
     __device__ __forceinline__ unsigned ballot(bool pr TMG_SITE_P) const { TMG_SITE_SET return __ballot_sync(0xffffffffu, pr); }
@@ -140,14 +182,9 @@ template <int RT, int CT> struct RBoard {
     }
     // ---- draw stream: words [4 pc_b0, 4 pc_b0 + 128) of stream 0 in s.wbuf -----------------------------------------------------------
     __device__ __forceinline__ void fill_cache(uint64_t b0) {
-        sync();                                           // earlier reads of the buffer are done
-        const uint64_t b = b0 + (uint64_t)lane;
-        uint32_t w[4];
-        philox4x32_10((uint32_t)b, (uint32_t)(b >> 32), gid, 0u, p.key0, p.key1, w);
-        *reinterpret_cast<uint4*>(&s.wbuf[4 * lane]) = *reinterpret_cast<uint4*>(w);
+        rb_fill_words(s.wbuf, b0, gid, p.key0, p.key1, lane);
         pc_b0 = b0;
         pc_valid = true;
-        sync();
     }
     __device__ __forceinline__ int injected_colour(int k) {
         const int v = injected_draw(p.inj, p.inj_len, env, (long long)dcur + k);
@@ -202,8 +239,10 @@ template <int RT, int CT> struct RBoard {
             const uint64_t start = dcur + (uint64_t)ps;
             int off = 0, nw = total - ps;
             if (!p.use_inj) {
-                const bool inside = pc_valid && start >= 4ull * pc_b0 && start + (uint64_t)nw <= 4ull * pc_b0 + 128ull;
-                if (!inside && !(pc_valid && (start >> 2) == pc_b0)) fill_cache(start >> 2);
+                // the cached window starts at word 4 pc_b0 <= dcur: positions relative to it fit 32 bits while it is valid
+                const long long rel = (long long)(start - 4ull * pc_b0);
+                const bool inside = pc_valid && rel >= 0 && rel + nw <= 128;
+                if (!inside && !(pc_valid && rel >= 0 && rel < 4)) fill_cache(start >> 2);
                 off = (int)(start - 4ull * pc_b0);
                 nw = min(nw, 128 - off);
             }
@@ -424,7 +463,7 @@ template <int RT, int CT> struct RBoard {
         if (best == BIG) return -1;
         return (best >> 5) * C + (best & 31);
     }
-    __device__ void enter_activation(int cell, int t, bool counted, int& sp) {
+    __device__ __forceinline__ void enter_activation(int cell, int t, bool counted, int& sp) {
         int r0, c0;
         cell_rc(cell, r0, c0);
         const int own_nz = cell_colour(r0, c0) != 0;
@@ -461,7 +500,14 @@ template <int RT, int CT> struct RBoard {
         stack_set(sp, frame(kind, cell, 0, mc));
         ++sp;
     }
-    __device__ void activate(int cell0, int t0, bool counted) {
+    __device__ __forceinline__ void activate(int cell, int t, bool counted) {   // one call, wherever a special is hit
+#if TMG_RB_OUTLINE
+        set_state(rb_activate_fn<RT, CT>(get_state(), &p, &s, lane, env, cell, t, (int)counted));
+#else
+        activate_impl(cell, t, counted);
+#endif
+    }
+    __device__ __forceinline__ void activate_impl(int cell0, int t0, bool counted) {
         int sp = 0;
         int e_cell = cell0, e_t = t0;
         bool e_counted = counted;
@@ -703,22 +749,49 @@ template <int RT, int CT> struct RBoard {
         n_new += ncq;
     }
 
+    __device__ __forceinline__ int general_impl(const RBScanPack& sp) {
+        Scan sc;
+        sc.rstar = sp.rstar; sc.mv = sp.mv; sc.hs = sp.hs; sc.hcells = sp.hcells; sc.m = sp.m; sc.vtop = sp.vtop; sc.has_v = sp.has_v != 0;
+        sc.bits.E = sp.E; sc.bits.D = sp.D; sc.bits.T = sp.T; sc.bits.S = sp.S;
+        const int n = build_line_table(sc);
+        classify_and_resolve(n);
+        return n;
+    }
+
     // one cascade round without gravity / refill (ref :369-373); returns the number of lines found
     __device__ __forceinline__ int resolve_round() {
+        const long long t0 = (TMG_RB_PROF && prof_on) ? clock64() : 0;
         const Scan sc = scan_lines();
         if (sc.rstar < 0) return 0;
         ++prof_rounds;
         int n = fast_round(sc);
-        if (n == 0) {
+        const long long t1 = (TMG_RB_PROF && prof_on) ? clock64() : 0;
+        if (n == 0) {                                                 // general path, out of line
             ++prof_general;
-            n = build_line_table(sc);
-            classify_and_resolve(n);
+            RBScanPack sp;
+            sp.rstar = sc.rstar; sp.mv = sc.mv; sp.hs = sc.hs; sp.hcells = sc.hcells; sp.m = sc.m; sp.vtop = sc.vtop; sp.has_v = sc.has_v;
+            sp.E = sc.bits.E; sp.D = sc.bits.D; sp.T = sc.bits.T; sp.S = sc.bits.S;
+#if TMG_RB_OUTLINE
+            const RBState st = rb_general_fn<RT, CT>(get_state(), &p, &s, lane, env, sp);
+            set_state(st);
+            n = st.aux;
+#else
+            n = general_impl(sp);
+#endif
         }
+        if (TMG_RB_PROF && prof_on) { prof_cyc[0] += (uint32_t)(t1 - t0); prof_cyc[1] += (uint32_t)(clock64() - t1); }
         return n;
     }
 
     // ---- combination_match (ref :600-719), as Board::combination -----------------------------------------------------------------------
-    __device__ void combination(int i1, int i2) {
+    __device__ __forceinline__ void combination(int i1, int i2) {
+#if TMG_RB_OUTLINE
+        set_state(rb_combination_fn<RT, CT>(get_state(), &p, &s, lane, env, i1, i2));
+#else
+        combination_impl(i1, i2);
+#endif
+    }
+    __device__ __forceinline__ void combination_impl(int i1, int i2) {
         n_act += 2;                                                   // ref :609
         int r1, c1, r2, c2;
         cell_rc(i1, r1, c1);
@@ -822,13 +895,30 @@ template <int RT, int CT> struct RBoard {
         const bool comb = (not01(t1) && not01(t2)) || t1 < 0 || t2 < 0;   // ref :357-359
         int elim = 0;
         fg_valid = false;
+        is_comb = comb;
+#if TMG_RB_SINGLE_FALL
+        if (comb) combination(i1, i2);                                // ref :361; its gravity + refill (ref :362-364) is the loop's first trip
+        bool pending = comb;
+#pragma unroll 1
+        for (;;) {                                                    // ref :367-376 (one call site of the round and of the fall)
+            if (!pending && resolve_round() == 0) break;
+            pending = false;
+            const long long t0 = (TMG_RB_PROF && prof_on) ? clock64() : 0;
+            elim += fall_and_refill();
+            if (TMG_RB_PROF && prof_on) prof_cyc[2] += (uint32_t)(clock64() - t0);
+        }
+#else
         if (comb) {
             combination(i1, i2);                                      // ref :361
             elim += fall_and_refill();                                // ref :362-364
         }
-        is_comb = comb;
 #pragma unroll 1
-        while (resolve_round() != 0) elim += fall_and_refill();       // ref :367-376
+        while (resolve_round() != 0) {                                // ref :367-376
+            const long long t0 = (TMG_RB_PROF && prof_on) ? clock64() : 0;
+            elim += fall_and_refill();
+            if (TMG_RB_PROF && prof_on) prof_cyc[2] += (uint32_t)(clock64() - t0);
+        }
+#endif
         return elim;                                                  // the caller adds num_new_specials (ref :378)
     }
 
@@ -863,3 +953,24 @@ template <int RT, int CT> struct RBoard {
     }
     __device__ __forceinline__ int special_count() { return radd(__popc(bits_S())); }
 };
+
+template <int RT, int CT> __device__ __noinline__ RBState rb_activate_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int cell, int t, int counted) {
+    RBoard<RT, CT> b(*sm, *pp, lane, env);
+    b.set_state(st);
+    b.activate_impl(cell, t, counted != 0);
+    return b.get_state();
+}
+template <int RT, int CT> __device__ __noinline__ RBState rb_general_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, RBScanPack sc) {
+    RBoard<RT, CT> b(*sm, *pp, lane, env);
+    b.set_state(st);
+    const int n = b.general_impl(sc);
+    RBState o = b.get_state();
+    o.aux = n;
+    return o;
+}
+template <int RT, int CT> __device__ __noinline__ RBState rb_combination_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int i1, int i2) {
+    RBoard<RT, CT> b(*sm, *pp, lane, env);
+    b.set_state(st);
+    b.combination_impl(i1, i2);
+    return b.get_state();
+}

@@ -8,7 +8,12 @@ package itself: gymnasium is optional (it is absent from the build image), and `
                               colourless_specials=["cookie"], colour_specials=["vertical_laser", "horizontal_laser", "bomb"])
 
 gives an `isinstance(envs, gymnasium.vector.VectorEnv)` whose arrays stay on the GPU (torch tensors, as documented for
-`TileMatchVecEnv`)."""
+`TileMatchVecEnv`).  The aliasing contract of `TileMatchVecEnv.step` applies to the subclass too: the returned reward /
+terminated / info tensors are views of the engine's buffers and are overwritten by the next call -- pass
+`copy_outputs=True` for gymnasium-style fresh arrays.
+
+gymnasium is not in the build image, so this module is exercised against a stand-in module only
+(tests/test_gym_compat.py); it has not been run against the real package."""
 from __future__ import annotations
 
 from .vec_env import ENV_ID, TileMatchVecEnv

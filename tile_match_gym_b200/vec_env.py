@@ -53,6 +53,10 @@ class TileMatchVecEnv:
                       inside the step; only the timing differs)
       obs             "int8" (aliases engine state, zero-copy), "int32" (reference dtype, one cast per call)
                       or "onehot" (OneHotWrapper planes, uint8)
+      copy_outputs    step() returns fresh copies of reward / terminated / the info tensors instead of views of the
+                      engine's buffers (see step(): the views are overwritten in place by the next call)
+      byte_planes     diagnostics: run the moves on the shared-memory byte-plane engine (TMG_FLAG_BYTE_PLANES) instead of
+                      the register-resident bit-plane engine; results are identical
     """
 
     metadata = {"render_modes": ["string"], "render_fps": 2}
@@ -61,7 +65,8 @@ class TileMatchVecEnv:
                  colourless_specials, colour_specials, seed: Optional[int] = 1, device="cuda:0",
                  autoreset: str = "next_step", refill: str = "philox", env_id_offset: int = 0,
                  compute_mask: bool = True, obs: str = "int8", max_reset_iters: int = 0,
-                 render_mode: str = "string", pregenerate: bool = True):
+                 render_mode: str = "string", pregenerate: bool = True, copy_outputs: bool = False,
+                 byte_planes: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("tile_match_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = nat.lib()
@@ -87,6 +92,8 @@ class TileMatchVecEnv:
         self.specials = nat.specials_mask(self.colourless_specials, self.colour_specials)
         self.onehot_planes = self._lib.tmg_onehot_planes(self.num_colours, self.specials)
         self.compute_mask = bool(compute_mask)
+        self.copy_outputs = bool(copy_outputs)
+        self._mirror_keep = None   # pinned host arrays bound as the host mirror (tmg_host_bind): kept alive while bound
 
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         torch.cuda.init()
@@ -95,7 +102,8 @@ class TileMatchVecEnv:
         cfg = nat.Config(C.sizeof(nat.Config), dev_index, self.num_envs, self.num_rows, self.num_cols,
                          self.num_colours, self.num_moves, self.specials, nat.AUTORESET[autoreset],
                          nat.REFILL[refill],
-                         (0 if compute_mask else nat.FLAG_NO_MASK) | (0 if pregenerate else nat.FLAG_NO_PREGEN),
+                         (0 if compute_mask else nat.FLAG_NO_MASK) | (0 if pregenerate else nat.FLAG_NO_PREGEN)
+                         | (nat.FLAG_BYTE_PLANES if byte_planes else 0),
                          int(max_reset_iters),
                          self.seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset)
         h = C.c_void_p()
@@ -163,11 +171,22 @@ class TileMatchVecEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def unbind_host_mirror(self) -> None:
+        """Detach the host mirror (tmg_host_bind(NULL)) and only then let go of the pinned arrays: the step kernels write
+        into them over PCIe, so they must outlive every launch that was issued while they were bound."""
+        if getattr(self, "_h", None) is not None and self._h and self._mirror_keep is not None:
+            nat.check(self._lib.tmg_host_bind(self._h, None, self._stream()), "tmg_host_bind")
+            torch.cuda.synchronize(self.device)
+        self._mirror_keep = None
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
-            torch.cuda.synchronize(self.device)
-            self._lib.tmg_destroy(self._h)
-            self._h = None
+            try:
+                self.unbind_host_mirror()
+            finally:
+                torch.cuda.synchronize(self.device)
+                self._lib.tmg_destroy(self._h)
+                self._h = None
 
     def __del__(self):
         try:
@@ -191,9 +210,10 @@ class TileMatchVecEnv:
         self.join()
         torch.cuda.synchronize(self.device)
         sd = {name: self._t[name].detach().cpu().clone() for name in self.STATE_FIELDS}
-        sd["config"] = {"seed": self.seed, "num_envs": self.num_envs, "num_rows": self.num_rows, "num_cols": self.num_cols,
-                        "num_colours": self.num_colours, "num_moves": self.num_moves, "specials": self.specials,
-                        "env_id_offset": self.env_id_offset}
+        sd["config"] = {"format": "tmg-state-2", "seed": self.seed, "num_envs": self.num_envs, "num_rows": self.num_rows,
+                        "num_cols": self.num_cols, "num_colours": self.num_colours, "num_moves": self.num_moves,
+                        "specials": self.specials, "env_id_offset": self.env_id_offset, "autoreset": self.autoreset_mode,
+                        "refill": self.refill}
         return sd
 
     def load_state_dict(self, sd: dict) -> None:
@@ -202,6 +222,11 @@ class TileMatchVecEnv:
         for k in ("num_envs", "num_rows", "num_cols", "num_colours", "num_moves", "specials", "env_id_offset"):
             if cfg[k] != getattr(self, k):
                 raise ValueError(f"state was saved with {k}={cfg[k]}, this env has {getattr(self, k)}")
+        # the autoreset mode decides what a saved terminal timer means and the refill mode where the next draws come
+        # from: a state only continues bit for bit under the modes it was saved with (older states carry neither)
+        for k, mine in (("autoreset", self.autoreset_mode), ("refill", self.refill)):
+            if k in cfg and cfg[k] != mine:
+                raise ValueError(f"state was saved with {k}={cfg[k]!r}, this env has {mine!r}")
         if cfg["seed"] != self.seed:
             self.set_seed(cfg["seed"])       # also forgets the boards generated ahead of time under the old key
         self.join()
@@ -254,7 +279,13 @@ class TileMatchVecEnv:
         return self._obs(), {"effective_actions": self.mask}
 
     def step(self, actions):
-        """tile_match_env.py:93-112 for every env.  actions: (N,) integer tensor."""
+        """tile_match_env.py:93-112 for every env.  actions: (N,) integer tensor.
+
+        Aliasing contract: obs["board"] (obs="int8"), obs["num_moves_left"], reward, terminated and every info tensor
+        are zero-copy VIEWS of the engine's device buffers -- like the reference's obs, which aliases live state
+        (tile_match_env.py:115) -- and are overwritten in place by the next step() / step_many() / rollout() / reset().
+        Code that keeps them across calls (`rewards.append(rew)`) must clone them, or construct the env with
+        copy_outputs=True, which returns fresh copies of the small per-env tensors (reward, terminated, info)."""
         a = torch.as_tensor(actions)
         if a.device != self.device or a.dtype != torch.int32 or not a.is_contiguous():
             a = a.to(device=self.device, dtype=torch.int32).contiguous()
@@ -269,6 +300,9 @@ class TileMatchVecEnv:
             "shuffled": self.shuffled,
             "effective_actions": self.mask,
         }
+        if self.copy_outputs:
+            info = {k: (v if k == "effective_actions" else v.clone()) for k, v in info.items()}
+            return self._obs(), self.reward.clone(), self.terminated.clone(), self.truncated, info
         return self._obs(), self.reward, self.terminated, self.truncated, info
 
     def step_many(self, actions):
@@ -418,7 +452,12 @@ class HostStepper:
         self.h2d_bytes = self.host["actions"].numel() * 4
         self.d2h_bytes = sum(t.numel() * t.element_size() for n, t in self.host.items() if n != "actions")
         if mirror:
+            if env._mirror_keep is not None:
+                raise RuntimeError("this env already has a host mirror bound; close() the other HostStepper first")
             nat.check(env._lib.tmg_host_bind(env._h, C.byref(self.io), env._stream()), "tmg_host_bind")
+            # the env owns the bound arrays from here on: the kernels of ANY later step write into them, whether or not
+            # this object is still alive (they are released by close() / env.unbind_host_mirror() / env.close())
+            env._mirror_keep = self.host
             self._mirrored = [n for n in ("board", "mask", "mask_bits") if n in self.host]
             scalars = [n for n in ("reward", "terminated", "num_moves_left") if n in self.host]
             # per step over PCIe: the mirrored scalars of every env + one entry of every mirrored array per env that
@@ -429,9 +468,17 @@ class HostStepper:
             self.d2h_bytes_per_changed_env += 4 if "reward" in scalars else 0
 
     def close(self):
+        """Unbinds the mirror (if any) and waits for the kernels that may still be writing into the pinned arrays."""
         if self.mirror:
-            nat.check(self.env._lib.tmg_host_bind(self.env._h, None, self.env._stream()), "tmg_host_bind")
             self.mirror = False
+            if self.env._mirror_keep is self.host:
+                self.env.unbind_host_mirror()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def effective_actions(self, i: int):
         """The reference's info["effective_actions"] list of env i from whichever mask form was copied back."""
@@ -465,8 +512,12 @@ class EpisodeStatistics:
     FIELDS = ("episodes", "return_sum", "length_sum", "steps", "specials_created", "specials_activated", "shuffles",
               "combination_matches")
 
-    def __init__(self, num_envs: int, device):
+    def __init__(self, num_envs: int, device, autoreset: str = "same_step"):
+        """autoreset: the env's mode.  Under "next_step" the call after a termination is the reset step (action ignored,
+        reward 0): like gymnasium's vector RecordEpisodeStatistics it is not counted as a step of the new episode."""
         self.device = torch.device(device)
+        self.autoreset = autoreset
+        self.prev_terminated = torch.zeros(num_envs, dtype=torch.bool, device=self.device)
         self.running_return = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
         self.running_length = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
         self.totals = torch.zeros(len(self.FIELDS), dtype=torch.int64, device=self.device)
@@ -474,13 +525,18 @@ class EpisodeStatistics:
     def update(self, reward, terminated, info) -> None:
         r = reward.to(torch.int64)
         term = terminated.to(torch.bool)
-        self.running_return += r
-        self.running_length += 1
+        if self.autoreset == "next_step":
+            live = (~self.prev_terminated).to(torch.int64)     # the step after a termination only resets the env
+            self.prev_terminated = term.clone()
+        else:
+            live = torch.ones_like(r)
+        self.running_return += r * live
+        self.running_length += live
         t = self.totals
         t[0] += term.sum()
         t[1] += (self.running_return * term).sum()
         t[2] += (self.running_length * term).sum()
-        t[3] += r.numel()
+        t[3] += live.sum()
         t[4] += info["num_new_specials"].to(torch.int64).sum()
         t[5] += info["num_specials_activated"].to(torch.int64).sum()
         t[6] += info["shuffled"].to(torch.int64).sum()
