@@ -184,6 +184,8 @@ int tmg_legal_mask(tmg_env *env, void *stream);
 int tmg_encode_onehot(tmg_env *env, uint8_t *out_dev, void *stream);
 /* same, float32 planes (the reference returns float64 0./1. values) */
 int tmg_encode_onehot_f32(tmg_env *env, float *out_dev, void *stream);
+/* same, float64 planes: the dtype OneHotWrapper.observation itself returns (np.zeros default, wrappers.py:57,64) */
+int tmg_encode_onehot_f64(tmg_env *env, double *out_dev, void *stream);
 
 int tmg_clear_status(tmg_env *env, void *stream);
 

@@ -1,6 +1,7 @@
 """Runs the product's DEVICE code (tile_match_gym_b200/csrc/tmg_device.cuh) on the CPU through the test-only
 lane emulator (tests/emu) against the golden traces and the oracle.  This is how kernel logic is debugged in a
 container without a GPU; the GPU parity tests (test_gpu_parity.py) are the real gate and do not use it."""
+import os
 import numpy as np
 import pytest
 
@@ -208,3 +209,39 @@ def test_emulated_primitives_vs_oracle(which, R, C, K, iters):
             if which in ("RESOLVE", "ACTIVATE", "COMBINE"):
                 assert o.counters == counters(), (which, si, it)
             assert int(e.status[0]) == 0
+
+
+def _decode_lines(words):
+    n = int(words[0])
+    ent = []
+    for i in range(n):
+        info, cells = int(words[1 + 2 * i]), int(words[2 + 2 * i])
+        kind, idx = (info >> 16) & 1, (info >> 17) & 31
+        bits = [b for b in range(32) if (cells >> b) & 1]
+        ent.append((info & 0xfff, sorted([(b, idx) for b in bits] if kind else [(idx, b) for b in bits])))
+    return [c for _, c in sorted(ent, key=lambda e: e[0])]
+
+
+def test_emulated_line_tables_list_for_list(monkeypatch):
+    """get_colour_lines (board.py:149-215) as the engines' line table, in the reference's list order: recorded calls of the
+    reference's tests (tests/board/test_match_detection.py:15-224 among them) through both engines of the emulated device
+    code (register-resident bit planes and byte planes; one board per warp)."""
+    import gzip
+    import json
+    from conftest import GOLDEN
+    from test_oracle_golden import _split_specials
+    monkeypatch.setenv("TMG_EMU_LANES32", "1")
+    with gzip.open(os.path.join(GOLDEN, "ref_test_calls.json.gz"), "rt") as f:
+        recs = [r for r in json.load(f) if r["fn"] == "get_colour_lines" and not r.get("err") and r["pre"] and r["pre"]["board"] is not None
+                and r["pre"]["C"] >= 2]
+    n_nonempty = 0
+    for rec in [r for i, r in enumerate(recs) if r["ret"] or i % 8 == 0]:
+        pre = rec["pre"]
+        cl, cs = _split_specials(pre["specials"])
+        e = EmuVecEnv(1, pre["R"], pre["C"], max(pre["K"], 1), 10, cl, cs)
+        e.reset(init_boards=np.asarray(pre["board"], dtype=np.int8)[None])
+        want = [sorted(tuple(c) for c in line) for line in rec["ret"]]
+        for byte_planes in (False, True):
+            assert _decode_lines(e.debug_lines(byte_planes)[0]) == want, (pre["R"], pre["C"], byte_planes)
+        n_nonempty += bool(want)
+    assert n_nonempty > 30, n_nonempty

@@ -80,6 +80,7 @@ EXPORTS = {
     "tmg_legal_mask": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_encode_onehot_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tmg_encode_onehot_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tmg_clear_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_join": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tmg_set_seed": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),

@@ -542,7 +542,7 @@ int tmg_legal_mask(tmg_env* e, void* stream) {
     return rc != TMG_OK ? rc : refresh_mirror(e, st);
 }
 
-static int onehot_launch(tmg_env* e, void* out, bool f32, void* stream) {
+static int onehot_launch(tmg_env* e, void* out, int elem_bytes, void* stream) {
     if (!e || !out) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     const Params p = e->p;
@@ -552,12 +552,14 @@ static int onehot_launch(tmg_env* e, void* out, bool f32, void* stream) {
     const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) return TMG_ERR_INVALID_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (f32) k_onehot<float><<<(unsigned)grid, block, 0, st>>>(p, static_cast<float*>(out), e->planes);
+    if (elem_bytes == 8) k_onehot<double><<<(unsigned)grid, block, 0, st>>>(p, static_cast<double*>(out), e->planes);
+    else if (elem_bytes == 4) k_onehot<float><<<(unsigned)grid, block, 0, st>>>(p, static_cast<float*>(out), e->planes);
     else k_onehot<uint8_t><<<(unsigned)grid, block, 0, st>>>(p, static_cast<uint8_t*>(out), e->planes);
     return last_error();
 }
-int tmg_encode_onehot(tmg_env* e, uint8_t* out_dev, void* stream) { return onehot_launch(e, out_dev, false, stream); }
-int tmg_encode_onehot_f32(tmg_env* e, float* out_dev, void* stream) { return onehot_launch(e, out_dev, true, stream); }
+int tmg_encode_onehot(tmg_env* e, uint8_t* out_dev, void* stream) { return onehot_launch(e, out_dev, 1, stream); }
+int tmg_encode_onehot_f32(tmg_env* e, float* out_dev, void* stream) { return onehot_launch(e, out_dev, 4, stream); }
+int tmg_encode_onehot_f64(tmg_env* e, double* out_dev, void* stream) { return onehot_launch(e, out_dev, 8, stream); }
 
 int tmg_clear_status(tmg_env* e, void* stream) {
     if (!e) return TMG_ERR_INVALID_ARG;

@@ -1922,7 +1922,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 // step reads one byte and never touches its board) and the outputs of a step that changes nothing.  Envs that need
 // board work -- an effective move, a new board, a zeroed mask -- go to the work list.
 #ifndef TMG_GATE_EPT
-#define TMG_GATE_EPT 4
+#define TMG_GATE_EPT 2   // measured on B200 (65 536 envs): 1 and 2 envs per thread 371-373 M steps/s, 4 envs per thread 362 M
 #endif
 enum { GATE_EPT = TMG_GATE_EPT };   // envs per thread of k_gate: four independent chains of dependent loads per thread, a quarter of the atomics
 __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) {

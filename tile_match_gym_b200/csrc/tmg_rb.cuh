@@ -212,7 +212,7 @@ template <int RT, int CT> struct RBoard {
     }
     // returns P - count_nonzero(type) of the round (ref :362, :374)
     __device__ __forceinline__ int fall_and_refill() {
-        int e, elim;
+        int e, gone;                                                  // this column: empties on top after the fall, type-0 cells
         if (fg_valid) {                                               // a fast-path round left at most one known gap per column
             fg_valid = false;
             const int len = fg_len, top = fg_top;
@@ -222,33 +222,58 @@ template <int RT, int CT> struct RBoard {
                 tw = (tw & keep) | ((tw & low) << len);
             }
             e = len;
-            elim = radd(len);                                         // the deleted cells are the type-0 cells
+            gone = len;                                               // the deleted cells are the type-0 cells
         } else {
-            elim = radd(__popc(bits_tz() & (lane < C ? 0xffffffffu : 0u)));
+            gone = lane < C ? __popc(bits_tz()) : 0;
             gravity_column();
             e = lane < C ? __popc(bits_empty()) : 0;
         }
-        unsigned m = ballot(e > 0);
-        if (!m) return elim;                                          // ref :238: no rng call when nothing is empty
-        const int maxe = rmax(e);
+        const unsigned m0 = ballot(e > 0);
+        const int elim = radd(gone);                                  // (only needed at the return: off the critical path)
+        if (!m0) return elim;                                         // ref :238: no rng call when nothing is empty
         const unsigned lt = lt_mask();
+        constexpr int RR = RT ? RT : PS;
+        // Common case: the cached window of the draw stream covers this refill whatever its size.  The rows are unrolled:
+        // the ballot of the next row is in flight while this row's word is loaded (a lone warp -- the longest cascade of
+        // a launch -- pays every dependent latency in full).
+        const long long rel = (long long)(dcur - 4ull * pc_b0);
+        if (!p.use_inj && pc_valid && rel >= 0 && rel + P <= 128) {
+            const int off = (int)rel;
+            int base = 0;
+            unsigned m = m0;
+#pragma unroll
+            for (int r = 0; r < RR; ++r) {                            // ref :239-241: k-th draw -> k-th empty cell, row-major
+                if (e > r) {
+                    const int k = 1 + (int)__umulhi(s.wbuf[off + base + __popc(m & lt)], (uint32_t)K);
+                    cw |= spread(k) << r;
+                    tw |= 1u << r;
+                }
+                base += __popc(m);
+                if (r + 1 < RR) {
+                    m = ballot(e > r + 1);
+                    if (!m) break;
+                }
+            }
+            dcur += (uint64_t)base;
+            return elim;
+        }
+        const int maxe = rmax(e);
         const int total = radd(e);
-        // ranks [ps, ps + nw) of this pass take words of the cached window; one pass unless the move draws > 125 tiles
+        // ranks [ps, ps + nw) of a pass take words of the cached window; one pass unless the move draws > 125 tiles
 #pragma unroll 1
         for (int ps = 0; ps < total;) {
             const uint64_t start = dcur + (uint64_t)ps;
             int off = 0, nw = total - ps;
             if (!p.use_inj) {
-                // the cached window starts at word 4 pc_b0 <= dcur: positions relative to it fit 32 bits while it is valid
-                const long long rel = (long long)(start - 4ull * pc_b0);
-                const bool inside = pc_valid && rel >= 0 && rel + nw <= 128;
-                if (!inside && !(pc_valid && rel >= 0 && rel < 4)) fill_cache(start >> 2);
+                const long long rl = (long long)(start - 4ull * pc_b0);
+                const bool inside = pc_valid && rl >= 0 && rl + nw <= 128;
+                if (!inside && !(pc_valid && rl >= 0 && rl < 4)) fill_cache(start >> 2);
                 off = (int)(start - 4ull * pc_b0);
                 nw = min(nw, 128 - off);
             }
             int base = 0;
 #pragma unroll 1
-            for (int r = 0; r < maxe; ++r) {                          // ref :239-241: k-th draw -> k-th empty cell, row-major
+            for (int r = 0; r < maxe; ++r) {
                 const unsigned mm = ballot(e > r);
                 if (e > r) {
                     const int rank = base + __popc(mm & lt);
@@ -382,9 +407,15 @@ template <int RT, int CT> struct RBoard {
             }
         }
         if (sc.mv) {                                                  // phase 2 (ref :198-214)
-            const int rmin_ = rmin(sc.has_v ? sc.vtop : 1 << 20);
+            // a crossing segment needs a horizontal run of >= 3 equal cells through a cell of a vertical line (see fast_round):
+            // only the rows where some line has one are visited, top to bottom
+            const unsigned El = from_left(sc.bits.E, 1), Er = from_right(sc.bits.E, 1), Ell = from_left(El, 1);
+            const unsigned cross = (sc.bits.E & Er) | (El & sc.bits.E) | (Ell & El);
+            const unsigned vrows = sc.has_v ? ((2u << rs) - 1u) & ~((1u << sc.vtop) - 1u) : 0u;
+            unsigned todo = ror(vrows & cross);
 #pragma unroll 1
-            for (int r = rmin_; r <= rs; ++r) {
+            for (; todo; todo &= todo - 1u) {
+                const int r = __ffs((int)todo) - 1;
                 const unsigned m = ballot((sc.bits.E >> r) & 1u);
                 const unsigned T = ballot((sc.bits.T >> r) & 1u);
                 const bool origin = sc.has_v && sc.vtop <= r;

@@ -352,8 +352,10 @@ class TileMatchVecEnv:
             nat.check(self._lib.tmg_encode_onehot(self._h, C.c_void_p(out.data_ptr()), self._stream()), "onehot")
         elif dtype == torch.float32:
             nat.check(self._lib.tmg_encode_onehot_f32(self._h, C.c_void_p(out.data_ptr()), self._stream()), "onehot")
+        elif dtype == torch.float64:       # the reference's own dtype (wrappers.py:57,64)
+            nat.check(self._lib.tmg_encode_onehot_f64(self._h, C.c_void_p(out.data_ptr()), self._stream()), "onehot")
         else:
-            raise ValueError("dtype must be uint8 or float32")
+            raise ValueError("dtype must be uint8, float32 or float64")
         return out
 
     def check_status(self, clear: bool = True) -> None:
