@@ -12,8 +12,9 @@ whose episode ended.  Workloads (BASELINE.json `configs`):
              65536 envs per GPU (weak scaling), uniform random actions.
   --config 3: 9x9, 6 colours, all specials, legal-move mask + one-hot observation every step, 131072 envs per GPU
              (1M envs over 8 GPUs).
-  --config 5: 32x32, 7 colours, all specials, 8192 envs per GPU; generate_board does not terminate for this shape in
-             the reference either, so every episode starts from injected line-free boards.
+  --config 5: 32x32, 7 colours, all specials, 8192 envs per GPU; the reference's generate_board does not terminate for
+             this shape, so every board comes from the on-device constructive line-free sampler
+             (TMG_FLAG_CONSTRUCTIVE_RESET; the CPU baseline runs the same contract) -- no host-side board injection.
 Episode phases are STAGGERED (env e starts at move e mod num_moves, as in any long-running RL loop), so every timed
 step carries exactly 1/num_moves of the batch's episode ends and board generations whatever --steps is; the line
 reports the episode ends counted inside the timed region and, beside `value`, the reset-free figure.
@@ -43,12 +44,13 @@ UNIT = "env-steps/s"
 
 # BASELINE.json configs that fit one GPU; bytes = SURVEY.md 8(d): 4P + 48 + A (+ (K+S)P with the one-hot observation)
 CONFIGS = {
-    2: dict(rows=10, cols=10, colours=4, envs=65536, onehot=False, inject=False, num_moves=30,
+    2: dict(rows=10, cols=10, colours=4, envs=65536, onehot=False, inject=False, constructive=False, num_moves=30,
             name="TileMatchEnv 10x10, 4 colours, specials=[vertical_laser,horizontal_laser,bomb,cookie]"),
-    3: dict(rows=9, cols=9, colours=6, envs=131072, onehot=True, inject=False, num_moves=30,
+    3: dict(rows=9, cols=9, colours=6, envs=131072, onehot=True, inject=False, constructive=False, num_moves=30,
             name="9x9, 6 colours, all specials, legal-move mask + one-hot obs (1M envs over 8 GPUs = 131072 per GPU)"),
-    5: dict(rows=32, cols=32, colours=7, envs=8192, onehot=False, inject=True, num_moves=30,
-            name="large-board stress 32x32, 7 colours, all specials, injected line-free initial boards"),
+    5: dict(rows=32, cols=32, colours=7, envs=8192, onehot=False, inject=False, constructive=True, num_moves=30,
+            name="large-board stress 32x32, 7 colours, all specials; boards from the on-device constructive line-free sampler "
+                 "(TMG_FLAG_CONSTRUCTIVE_RESET, not the reference's generate_board, which never returns for this shape)"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch of config 2 (ncu --set full, profiles/): no-op steps
 # never load their board and writes stay in the 126 MB L2 within a launch
@@ -147,8 +149,10 @@ def cpu_port_throughput(wl, threads, target_s=10.0):
         dt = time.perf_counter() - t0
         return num_envs * steps / dt, dt, num_envs, steps
     num_envs = max(threads * 256, 2048)
+    if wl["constructive"]:
+        num_envs = max(threads * 16, 128)
     o = OracleVecEnv(num_envs, wl["rows"], wl["cols"], wl["colours"], moves, ALL_CL, ALL_CS, seed=SEED, autoreset="same_step",
-                     num_threads=threads)
+                     num_threads=threads, constructive_reset=wl["constructive"])
     o.reset()
     t0 = time.perf_counter()
     o.rollout(moves, 99, 0)                          # one whole episode: warm-up + calibration
@@ -191,7 +195,7 @@ def python_reference_throughput(wl, target_s=8.0):
     (the build container; it is absent on the GPU box) -- returns a one-line reason otherwise."""
     try:
         from oracle.ref_loader import reference_available
-        if wl["inject"]:
+        if wl["inject"] or wl["constructive"]:
             return {"unavailable": "generate_board does not terminate for this shape in the reference (SURVEY 0.7)"}
         if not reference_available():
             return {"unavailable": "reference tree not present on this machine (it exists only in the build container); "
@@ -299,6 +303,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from tile_match_gym_b200.numa import bind_to_gpu_node
+    numa_node = bind_to_gpu_node(local_rank)        # pinned host arrays and the driving thread on the GPU's NUMA node
     if args.step_stream_priority:
         torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.step_stream_priority))
     if world > 1:
@@ -316,7 +322,8 @@ def main():
     def make_env(moves):
         env = TileMatchVecEnv(n_local, R, Cc, K, moves, ALL_CL, ALL_CS, seed=SEED, device=dev,
                               autoreset="disabled" if inject else "same_step", env_id_offset=rank * n_local,
-                              obs="onehot" if wl["onehot"] else "int8", byte_planes=args.byte_planes)
+                              obs="onehot" if wl["onehot"] else "int8", byte_planes=args.byte_planes,
+                              constructive_reset=wl["constructive"])
         if inject:
             env.reset(options={"init_boards": init_boards})
         else:
@@ -463,23 +470,25 @@ def main():
     # of the envs it changed straight into the pinned arrays.  The full-copy forms are reported beside it.
     if inject:
         env.reset(options={"init_boards": init_boards})
-    hs, e2e_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"), mirror=True)
+    board_out = "board_packed" if K <= 15 else "board"     # one byte per cell (colour | type << 4): half the PCIe bytes
+    hs, e2e_ms = time_host_path((board_out, "reward", "terminated", "mask_bits", "num_moves_left"), mirror=True)
     if args.skip_e2e:
-        hs_full, e2e_full_ms, hs_bytes, e2e_bytes_ms = hs, e2e_ms, hs, e2e_ms
+        hs_planes, e2e_planes_ms, hs_full, e2e_full_ms, hs_bytes, e2e_bytes_ms = hs, e2e_ms, hs, e2e_ms, hs, e2e_ms
     else:
+        hs_planes, e2e_planes_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"), mirror=True)
         hs_full, e2e_full_ms = time_host_path(("board", "reward", "terminated", "mask_bits", "num_moves_left"))
         hs_bytes, e2e_bytes_ms = time_host_path(("board", "reward", "terminated", "mask", "num_moves_left"))
     clocks = sampler.summary() if rank == 0 else None
 
     # max over ranks
-    vals = [total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms or 0.0, rollout_mask_ms or 0.0, no_reset_ms or 0.0]
+    vals = [total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms or 0.0, rollout_mask_ms or 0.0, no_reset_ms or 0.0, e2e_planes_ms]
     if world > 1:
         t = torch.tensor(vals, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = t.tolist()
         cnt = torch.tensor([status_bad, episode_ends], device=dev); dist.all_reduce(cnt)
         status_bad, episode_ends = int(cnt[0].item()), int(cnt[1].item())
-    total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms_, rollout_mask_ms_, no_reset_ms_ = vals
+    total_ms, e2e_ms, e2e_bytes_ms, e2e_full_ms, rollout_ms_, rollout_mask_ms_, no_reset_ms_, e2e_planes_ms = vals
     n_global = n_local * world
     value = n_global * args.steps / (total_ms * 1e-3)
     e2e_value = n_global * e2e_steps / (e2e_ms * 1e-3)
@@ -496,10 +505,14 @@ def main():
             "episode_ends_expected": n_global * args.steps / num_moves,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": hs.h2d_bytes * world,
                     "d2h_bytes_per_step": hs.d2h_bytes * world, "steps": e2e_steps,
-                    "returns": "board,reward,terminated,mask(bit-packed),num_moves_left in pinned host memory, complete and "
-                               "current after every step, stream synchronised per step; board and mask are a host mirror "
-                               "(tmg_host_bind) that the step kernel updates in place for the envs it changed "
-                               f"({hs.avg_changed / n_local:.3f} of the envs per step), scalars are copied in full",
+                    "returns": "board (one byte per cell: colour | type << 4),reward,terminated,mask(bit-packed),num_moves_left in "
+                               "pinned host memory, complete and current after every step, the call returns when the stream has "
+                               "finished; board and mask are a host mirror (tmg_host_bind) that the step kernel updates in place "
+                               f"for the envs it changed ({hs.avg_changed / n_local:.3f} of the envs per step), the scalars of "
+                               "every env are written by the gate kernel",
+                    "board_as_byte_planes": {"value": n_global * e2e_steps / (e2e_planes_ms * 1e-3),
+                                             "d2h_bytes_per_step": hs_planes.d2h_bytes * world,
+                                             "what": "the same with the board mirrored as the reference's two int8 planes"},
                     "full_copy_every_step": {"value": n_global * e2e_steps / (e2e_full_ms * 1e-3),
                                              "d2h_bytes_per_step": hs_full.d2h_bytes * world},
                     "full_copy_byte_mask": {"value": n_global * e2e_steps / (e2e_bytes_ms * 1e-3),
@@ -514,6 +527,7 @@ def main():
             "clocks": clocks,
             "step_ms": {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms)},
             "drain_ms": drain_ms, "wall_s": t_wall, "status_flags_set": status_bad,
+            "numa_node": numa_node,
             "engine": "byte planes (TMG_FLAG_BYTE_PLANES)" if args.byte_planes else "register-resident bit planes where the shape allows",
         }
         if no_reset_ms is not None:

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define TMG_ABI_VERSION 1
+#define TMG_ABI_VERSION 2   /* 2: tmg_host_io.board_packed */
 
 /* return codes */
 #define TMG_OK 0
@@ -84,6 +84,15 @@ extern "C" {
 #define TMG_FLAG_NO_PREGEN 2u      /* generate every board inside tmg_step instead of ahead of time on a side stream */
 #define TMG_FLAG_BYTE_PLANES 4u    /* run the moves on the byte planes in shared memory instead of the register-resident
                                       bit-plane engine (same results; diagnostics / A-B measurements) */
+
+#define TMG_FLAG_CONSTRUCTIVE_RESET 8u /* NOT the reference's generate_board: every board (tmg_reset, autoreset, pool) comes
+                                      from a constructive line-free sampler, for shapes where the reference's redraw loop
+                                      (board.py:99-109) does not terminate (e.g. 32x32 / 7 colours).  Board j of env e:
+                                      cells in row-major order, each takes the next colour 1 + mulhi32(W5(k), K), k = 0, 1,
+                                      ..., W5(k) = Philox4x32-10(key, ctr = (k>>2, j, e, 5))[k&3], that does not complete a
+                                      triple with the two cells to its left or the two above it (at most 64 draws per cell,
+                                      then TMG_ST_RESET_CAP); all types 1; a board without a possible move is drawn again
+                                      from where the stream stands.  The env's refill stream is not touched. */
 
 #define TMG_MAX_ROWS 32
 #define TMG_MAX_COLS 32
@@ -212,12 +221,14 @@ typedef struct tmg_host_io {
     int32_t *num_specials_activated; /* out [N] or NULL */
     uint8_t *shuffled;               /* out [N] or NULL */
     uint32_t *status;                /* out [N] or NULL */
+    uint8_t *board_packed;           /* out [N][R][C] or NULL: the board as one byte per cell, colour | (type & 7) << 4
+                                        (cookie type -1 -> 7), half the PCIe bytes of `board`; needs num_colours <= 15 */
 } tmg_host_io;
 int tmg_step_host(tmg_env *env, const tmg_host_io *io, void *stream);
 
 /* Host mirror: the fast form of the host-buffer path.  Registers the page-locked host arrays of `io` (cudaHostAlloc /
- * cudaHostRegister memory, 16-byte aligned; any of them may be NULL) as a mirror of buffers.board / buffers.mask / the
- * bit-packed mask / reward / terminated / num_moves_left.  The
+ * cudaHostRegister memory, 16-byte aligned; any of them may be NULL) as a mirror of buffers.board (as byte planes and / or
+ * packed, one byte per cell) / buffers.mask / the bit-packed mask / reward / terminated / num_moves_left.  The
  * call copies the current contents in full; from then on tmg_step's kernels write, straight into the arrays over PCIe,
  * the board and mask entries of exactly those envs whose board or mask they changed (a step that changes nothing moves
  * no board bytes) and the three per-env scalars of every env (coalesced), and tmg_reset / tmg_legal_mask /

@@ -44,7 +44,8 @@ class _VecConfig(C.Structure):
     _fields_ = [("num_envs", C.c_int32), ("num_rows", C.c_int32), ("num_cols", C.c_int32),
                 ("num_colours", C.c_int32), ("num_moves", C.c_int32), ("specials", C.c_uint32),
                 ("autoreset", C.c_int32), ("refill_mode", C.c_int32), ("seed", C.c_uint64),
-                ("env_id_offset", C.c_uint64), ("max_reset_iters", C.c_int64), ("num_threads", C.c_int32)]
+                ("env_id_offset", C.c_uint64), ("max_reset_iters", C.c_int64), ("num_threads", C.c_int32),
+                ("flags", C.c_uint32)]
 
 
 class _VecBuffers(C.Structure):
@@ -316,13 +317,13 @@ class OracleVecEnv:
 
     def __init__(self, num_envs, num_rows, num_cols, num_colours, num_moves, colourless_specials=(),
                  colour_specials=(), seed=1, autoreset="disabled", refill="philox", env_id_offset=0,
-                 max_reset_iters=16384, num_threads=1):
+                 max_reset_iters=16384, num_threads=1, constructive_reset=False):
         self.L = lib()
         modes = {"disabled": 0, "next_step": 1, "same_step": 2}
         self.cfg = _VecConfig(int(num_envs), int(num_rows), int(num_cols), int(num_colours), int(num_moves),
                               specials_mask(colourless_specials, colour_specials), modes[autoreset],
                               {"philox": 0, "injected": 1}[refill], int(seed), int(env_id_offset),
-                              int(max_reset_iters), int(num_threads))
+                              int(max_reset_iters), int(num_threads), 8 if constructive_reset else 0)
         self.h = self.L.tmgo_vec_create(C.byref(self.cfg))
         self.N, self.R, self.Cc, self.K = int(num_envs), int(num_rows), int(num_cols), int(num_colours)
         self.A = 2 * self.R * self.Cc - self.R - self.Cc

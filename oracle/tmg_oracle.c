@@ -43,6 +43,7 @@ struct tmgo_board {
     /* episode-indexed reset streams (oracle/stream.py): board j of an env is a pure function of (seed, env, j) */
     int32_t episode;
     int in_reset;
+    int constructive;                               /* generate_board -> constructive sampler (not the reference) */
     uint64_t rdc, rsc;
     const uint8_t *inj;
     int64_t inj_len;
@@ -825,8 +826,37 @@ static int playability_loop(tmgo_board *b, int have_lines) {
     return shuffled;
 }
 
+void tmgo_board_set_constructive(tmgo_board *b, int on) { b->constructive = on; }
+
+/* NOT the reference's algorithm: the product's TMG_FLAG_CONSTRUCTIVE_RESET contract (include/tmg_b200.h), restated.
+ * Cells in row-major order; each takes the next colour of stream 5 of the board that does not complete a triple with the
+ * two cells to its left or the two above it (at most 64 draws); a board without a possible move is drawn again. */
+static void generate_constructive(tmgo_board *b) {
+    int R = b->R, C = b->C;
+    uint64_t k = 0;
+    int64_t attempts = 0;
+    for (;;) {
+        for (int i = 0; i < b->P; i++) b->type[i] = 1;
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) {
+                int fv = (r >= 2 && b->colour[(r - 1) * C + c] == b->colour[(r - 2) * C + c]) ? b->colour[(r - 1) * C + c] : -1;
+                int fh = (c >= 2 && b->colour[r * C + c - 1] == b->colour[r * C + c - 2]) ? b->colour[r * C + c - 1] : -1;
+                int col = 1;
+                for (int tries = 0;; tries++) {
+                    col = 1 + (int)(((uint64_t)reset_word(b, 5, k++) * (uint64_t)b->K) >> 32);
+                    if (col != fv && col != fh) break;
+                    if (tries >= 63) { b->status |= TMGO_ST_RESET_CAP; break; }
+                }
+                b->colour[r * C + c] = col;
+            }
+        if (tmgo_possible_move(b)) break;
+        if (++attempts >= (b->iter_cap > 0 ? b->iter_cap : 16384)) { b->status |= TMGO_ST_RESET_CAP; break; }
+    }
+}
+
 void tmgo_generate_board(tmgo_board *b) {           /* ref board.py:95-112 */
     b->episode++;
+    if (b->constructive) { generate_constructive(b); return; }
     b->in_reset = !b->use_inj;                      /* injected draws are one sequential stream */
     b->rdc = b->rsc = 0;
     for (int i = 0; i < b->P; i++) b->type[i] = 1;
@@ -942,6 +972,7 @@ tmgo_vec *tmgo_vec_create(const tmgo_vec_config *cfg) {
     v->worker = (tmgo_board **)calloc((size_t)v->nthreads, sizeof(tmgo_board *));
     for (int t = 0; t < v->nthreads; t++) {
         v->worker[t] = tmgo_board_create(R, C, cfg->num_colours, cfg->specials);
+        if (v->worker[t]) v->worker[t]->constructive = (cfg->flags & TMGO_FLAG_CONSTRUCTIVE_RESET) != 0;
         tmgo_board_set_iter_cap(v->worker[t], cfg->max_reset_iters);
     }
     return v;

@@ -45,6 +45,8 @@ typedef struct tmgo_board tmgo_board;
 
 /* ---- single board (mirrors reference class Board, board.py:41-726) ---- */
 tmgo_board *tmgo_board_create(int num_rows, int num_cols, int num_colours, uint32_t specials);
+/* NOT the reference: generate_board is replaced by the constructive line-free sampler (include/tmg_b200.h) */
+void tmgo_board_set_constructive(tmgo_board *b, int on);
 void tmgo_board_destroy(tmgo_board *b);
 /* stream: Philox (seed, env_id) or injected pre-drawn colours (draws may be NULL) */
 void tmgo_board_set_stream(tmgo_board *b, uint64_t seed, uint32_t env_id, uint64_t draw_cursor,
@@ -106,7 +108,9 @@ typedef struct tmgo_vec_config {
     uint64_t env_id_offset;
     int64_t max_reset_iters; /* 0 = unlimited */
     int32_t num_threads;     /* host threads used by tmgo_vec_step/reset */
+    uint32_t flags;          /* TMGO_FLAG_* */
 } tmgo_vec_config;
+#define TMGO_FLAG_CONSTRUCTIVE_RESET 8u /* the product's TMG_FLAG_CONSTRUCTIVE_RESET contract (include/tmg_b200.h) */
 
 typedef struct tmgo_vec_buffers { /* host arrays owned by the oracle, SoA over envs */
     int8_t *board;            /* [N][2][R][C] */

@@ -48,6 +48,7 @@ def lib():
         L.emu_destroy.argtypes = [C.c_void_p]
         L.emu_get_buffers.argtypes = [C.c_void_p, C.POINTER(_Bufs)]
         L.emu_host_bind.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.emu_host_bind_packed.argtypes = [C.c_void_p, C.c_void_p]
         L.emu_set_injected_draws.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.emu_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_void_p]
@@ -107,6 +108,8 @@ class EmuVecEnv:
         self.h_moves_left = self.num_moves_left.copy()
         self.L.emu_host_bind(self.h, _ptr(self.h_board), _ptr(self.h_mask), _ptr(self.h_mask_bits), _ptr(self.h_reward),
                              _ptr(self.h_terminated), _ptr(self.h_moves_left))
+        self.h_board_packed = ((self.board[:, 0] & 15) | ((self.board[:, 1] & 7) << 4)).astype(np.uint8).copy()
+        self.L.emu_host_bind_packed(self.h, _ptr(self.h_board_packed))
 
     def reset(self, reset_mask=None, init_boards=None):
         m = None if reset_mask is None else np.ascontiguousarray(reset_mask, dtype=np.uint8)

@@ -235,6 +235,7 @@ void emu_get_buffers(void* h, emu_buffers* o) {
     o->num_new_specials = p.new_specials; o->num_specials_activated = p.activated; o->shuffled = p.shuffled;
     o->mask = p.mask; o->num_moves_left = p.moves_left; o->status = p.status; o->episode = p.episode;
 }
+void emu_host_bind_packed(void* h, uint8_t* board_packed) { ((EmuEnv*)h)->p.h_board_packed = board_packed; }
 void emu_host_bind(void* h, int8_t* board, uint8_t* mask, uint8_t* mask_bits, int32_t* reward, uint8_t* terminated,
                    int32_t* moves_left) {   // the mirror is ordinary memory here
     Params& p = ((EmuEnv*)h)->p;

@@ -55,6 +55,7 @@ static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x)
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline long long clock64() { return 0; }
 static inline void __threadfence() {}
+template <typename T> static inline T __ldcg(const T* p) { return *p; }
 template <typename T> static inline T atomicAdd(T* a, T v) { T o = *a; *a += v; return o; }
 using std::max;
 using std::min;

@@ -26,7 +26,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in include/tmg_b200.h but not exported"
     assert set(_native.EXPORTS) == set(names)
     lib = _native.lib()
-    assert lib.tmg_abi_version() == 1
+    assert lib.tmg_abi_version() == 2
     assert lib.tmg_num_actions(10, 10) == 180 and lib.tmg_num_actions(9, 9) == 144 and lib.tmg_num_actions(32, 32) == 1984
     assert lib.tmg_onehot_planes(6, 15) == 10 and lib.tmg_onehot_planes(5, 0) == 5
     assert lib.tmg_status_string(1 | 8).decode() == "bad_action|reset_cap"

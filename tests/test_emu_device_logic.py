@@ -109,6 +109,7 @@ def test_emulated_step_many_equals_single_steps(R, C, K, moves, autoreset, T):
         for f in fields:
             assert np.array_equal(getattr(e, f), getattr(o, f)), (window, f)
         assert np.array_equal(e.h_board, e.board) and np.array_equal(e.h_mask, e.mask)
+        assert np.array_equal(e.h_board_packed, ((e.board[:, 0] & 15) | ((e.board[:, 1] & 7) << 4)).astype(np.uint8))
         assert np.array_equal(e.h_reward, e.reward) and np.array_equal(e.h_terminated, e.terminated)
         assert np.array_equal(e.h_moves_left, e.num_moves_left)
         e.step(acts[0]); o.step(acts[0])      # single steps and rollouts interleave
@@ -129,6 +130,7 @@ def test_emulated_host_mirror_tracks_device_state(R, C, K, moves, autoreset):
             e.reset(); e.host_bind()
         e.step(rng.integers(0, e.A, N).astype(np.int32))
         assert np.array_equal(e.h_board, e.board), t
+        assert np.array_equal(e.h_board_packed, ((e.board[:, 0] & 15) | ((e.board[:, 1] & 7) << 4)).astype(np.uint8)), t
         assert np.array_equal(e.h_mask, e.mask), t
         assert np.array_equal(e.h_mask_bits, np.packbits(e.mask, axis=1, bitorder="little")), t
         assert np.array_equal(e.h_reward, e.reward) and np.array_equal(e.h_terminated, e.terminated), t
@@ -245,3 +247,26 @@ def test_emulated_line_tables_list_for_list(monkeypatch):
             assert _decode_lines(e.debug_lines(byte_planes)[0]) == want, (pre["R"], pre["C"], byte_planes)
         n_nonempty += bool(want)
     assert n_nonempty > 30, n_nonempty
+
+
+@pytest.mark.parametrize("N,R,Cc,K,moves", [(6, 10, 10, 4, 4), (3, 32, 32, 7, 3), (8, 5, 5, 3, 3), (4, 16, 12, 3, 3)])
+def test_emulated_constructive_reset_matches_oracle(N, R, Cc, K, moves):
+    """TMG_FLAG_CONSTRUCTIVE_RESET (NOT reference behaviour): the constructive line-free sampler of the device
+    code and its restatement in the oracle produce the same boards -- at reset, at every autoreset and through the pool --
+    and the boards are line-free with a possible move, also for 32x32 / 7 colours where generate_board never returns."""
+    cl, cs = ["cookie"], ["vertical_laser", "horizontal_laser", "bomb"]
+    e = EmuVecEnv(N, R, Cc, K, moves, cl, cs, seed=9, autoreset="same_step", flags=8)
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, cl, cs, seed=9, autoreset="same_step", num_threads=1, constructive_reset=True)
+    e.reset(); o.reset()
+    assert np.array_equal(e.board, o.board) and np.array_equal(e.mask, o.mask)
+    b = o.board[:, 0]
+    assert (o.board[:, 1] == 1).all() and b.min() >= 1 and b.max() <= K and o.mask.any(axis=1).all()
+    assert not ((b[:, :, :-2] == b[:, :, 1:-1]) & (b[:, :, 1:-1] == b[:, :, 2:])).any()
+    assert not ((b[:, :-2] == b[:, 1:-1]) & (b[:, 1:-1] == b[:, 2:])).any()
+    rng = np.random.default_rng(0)
+    for t in range(3 * moves + 1):
+        a = rng.integers(0, e.A, size=N).astype(np.int32)
+        e.step(a); o.step(a)
+        assert np.array_equal(e.board, o.board) and np.array_equal(e.reward, o.reward) and np.array_equal(e.mask, o.mask), t
+        assert np.array_equal(e.draw_cursor, o.draw_cursor)
+    assert (e.status == 0).all() and (o.status == 0).all() and int(o.episode.max()) == 3

@@ -78,7 +78,7 @@ def assert_same(g, o, ctx, fields=FIELDS):
 def test_library_loaded_and_is_the_cuda_one():
     from tile_match_gym_b200 import _native
     L = _native.lib()
-    assert L.tmg_abi_version() == 1
+    assert L.tmg_abi_version() == 2
     assert os.path.basename(_native.LIB_PATH) == "libtmg_b200.so"
 
 

@@ -367,3 +367,54 @@ def test_host_mirror_outlives_a_dropped_stepper():
     assert np.array_equal(hs2.host["board"].numpy(), env.board.cpu().numpy())
     env.close()                                          # unbinds before destroying the handle
     assert env._mirror_keep is None
+
+
+@pytest.mark.parametrize("N,R,Cc,K,moves,autoreset", [(4096, 32, 32, 7, 6, "same_step"), (2048, 10, 10, 4, 5, "next_step"),
+                                                     (1024, 20, 20, 5, 4, "same_step")])
+def test_constructive_reset_on_device(N, R, Cc, K, moves, autoreset):
+    """SURVEY 8f.2 / TMG_FLAG_CONSTRUCTIVE_RESET (NOT reference behaviour): config 5's shape with NO host-side board injection
+    -- boards from the on-device constructive line-free sampler at reset, at every autoreset and through the pool -- against
+    the same contract restated in the oracle; boards are line-free, all normal, and have a possible move."""
+    torch = _torch()
+    g = GpuAdapter(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=14, autoreset=autoreset, constructive_reset=True))
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=14, autoreset=autoreset, num_threads=os.cpu_count() or 8,
+                         constructive_reset=True)
+    g.reset(); o.reset()
+    assert_same(g, o, "reset")
+    b = o.board[:, 0]
+    assert (o.board[:, 1] == 1).all() and b.min() >= 1 and b.max() <= K and o.mask.any(axis=1).all()
+    assert not ((b[:, :, :-2] == b[:, :, 1:-1]) & (b[:, :, 1:-1] == b[:, :, 2:])).any()
+    assert not ((b[:, :-2] == b[:, 1:-1]) & (b[:, 1:-1] == b[:, 2:])).any()
+    rng = np.random.default_rng(6)
+    for t in range(3 * moves + 2):
+        a = rng.integers(0, o.A, size=N).astype(np.int32)
+        g.step(a); o.step(a)
+        assert_same(g, o, f"step {t}")
+    assert int(o.status.sum()) == 0 and int(o.episode.max()) >= 2
+
+
+@pytest.mark.parametrize("mirror", [True, False])
+def test_packed_board_host_output(mirror):
+    """tmg_host_io.board_packed: the board as one byte per cell (colour | (type & 7) << 4), as a host mirror the step
+    kernel writes in place and as a plain copy -- decoded, it is the board of every env after every step."""
+    torch = _torch()
+    from tile_match_gym_b200 import HostStepper
+    N, R, Cc, K, moves = 3000, 10, 10, 4, 7
+    env = make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=6, autoreset="same_step")
+    o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=6, autoreset="same_step", num_threads=8)
+    env.reset(); o.reset()
+    hs = HostStepper(env, outputs=("board_packed", "reward", "terminated", "mask_bits", "num_moves_left"), mirror=mirror)
+    rng = np.random.default_rng(8)
+    for t in range(3 * moves + 1):
+        m = o.mask.astype(np.float64) + 1e-9
+        u = rng.random((N, 1)) * m.sum(axis=1, keepdims=True)
+        a = (np.cumsum(m, axis=1) < u).sum(axis=1).clip(0, o.A - 1).astype(np.int32)
+        out = hs.step(a); o.step(a)
+        assert np.array_equal(hs.board(), o.board), t
+        assert np.array_equal(out["reward"].numpy(), o.reward) and np.array_equal(out["terminated"].numpy(), o.terminated), t
+        assert np.array_equal(np.unpackbits(out["mask_bits"].numpy(), axis=1, bitorder="little")[:, :o.A], o.mask), t
+    hs.close()
+    big = make_gpu(8, 5, 5, 16, 5, ALL_CL, ALL_CS, seed=1, autoreset="disabled")   # 16 colours do not fit the nibble
+    big.reset()
+    with pytest.raises(RuntimeError):
+        HostStepper(big, outputs=("board_packed",), mirror=True)

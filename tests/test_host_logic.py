@@ -71,3 +71,27 @@ def test_episode_statistics_allreduce_gloo_world2():
     assert res[0]["episodes"] == 20 and res[0]["steps"] == 60
     assert res[0]["return_sum"] == int(all_r.sum()) and res[0]["length_sum"] == 60
     assert res[0]["specials_created"] == 60 and res[0]["combination_matches"] == 20
+
+
+def test_numa_helpers_parse_and_degrade():
+    from tile_match_gym_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa._parse_cpulist("") == set()
+    assert numa.gpu_numa_node(0) is None or isinstance(numa.gpu_numa_node(0), int)   # no GPU here: None, never raises
+
+
+def test_episode_statistics_next_step_skips_the_reset_step():
+    """gymnasium's vector RecordEpisodeStatistics convention: under next_step autoreset the call after a termination only
+    resets the env -- it is not a step of the new episode."""
+    import torch
+    from tile_match_gym_b200.vec_env import EpisodeStatistics
+    st = EpisodeStatistics(2, "cpu", autoreset="next_step")
+    zeros = {k: torch.zeros(2, dtype=torch.int32) for k in ("num_new_specials", "num_specials_activated", "shuffled", "is_combination_match")}
+    seq = [([3, 1], [0, 0]), ([2, 0], [1, 0]), ([0, 4], [0, 1]), ([5, 0], [0, 0]), ([1, 2], [1, 0])]
+    # env 0: episode of 2 steps (return 5), reset step, then an episode of 2 steps (5 + 1 = 6)
+    # env 1: episode of 3 steps (return 5), reset step, one live step so far
+    for r, t in seq:
+        st.update(torch.tensor(r), torch.tensor(t, dtype=torch.bool), zeros)
+    out = st.allreduce()
+    assert out["episodes"] == 3 and out["return_sum"] == 5 + 5 + 6 and out["length_sum"] == 2 + 3 + 2
+    assert out["steps"] == 10 - 2          # two of the ten env-steps were reset steps

@@ -26,6 +26,7 @@ POLICY = {"uniform": 1, "mask": 2}
 FLAG_NO_MASK = 1
 FLAG_NO_PREGEN = 2
 FLAG_BYTE_PLANES = 4
+FLAG_CONSTRUCTIVE_RESET = 8
 OP_BYTE_PLANES = 0x100
 LINES_WORDS = 65
 
@@ -54,7 +55,7 @@ class Buffers(C.Structure):
 
 
 HOST_IO_FIELDS = ["actions", "board", "reward", "terminated", "mask", "mask_bits", "num_moves_left", "is_combination_match",
-                  "num_new_specials", "num_specials_activated", "shuffled", "status"]
+                  "num_new_specials", "num_specials_activated", "shuffled", "status", "board_packed"]
 
 
 class HostIO(C.Structure):
@@ -144,9 +145,11 @@ def lib():
                                "(tile_match_gym_b200 has no CPU fallback)")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
+            if not hasattr(L, name) and "TMG_B200_LIB" in os.environ:
+                continue
             f = getattr(L, name)
             f.restype, f.argtypes = res, args
-        if L.tmg_abi_version() != 1:
+        if L.tmg_abi_version() != 2 and "TMG_B200_LIB" not in os.environ:   # (A/B builds of older sources are loaded as they are)
             raise RuntimeError("libtmg_b200.so ABI version mismatch")
         _lib = L
     return _lib

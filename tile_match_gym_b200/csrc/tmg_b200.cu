@@ -19,6 +19,7 @@ struct tmg_env {
     int planes;     // one-hot planes
     int32_t* actions_dev;  // staging for tmg_step_host
     uint8_t* mask_bits_dev;
+    uint8_t* board_packed_dev;   // staging for the full refresh of a packed board mirror
     void* base;     // one allocation backs every buffer
     size_t bytes;
     // board pool: k_pregen runs on ONE side stream (refills are served strictly in request order, so the pool entry of an
@@ -37,10 +38,11 @@ struct tmg_env {
     long long step_count;     // number of tmg_step calls so far (parity selects the work-list counters)
     int persistent_blocks;    // resident-block slots of the device for k_work / k_pregen (persistent groups)
     int pregen_grid_cap;      // diagnostics: cap on the blocks of a k_pregen launch
+    bool pregen_one_shot;     // diagnostics: short-lived k_pregen blocks (one board per group), see Params::pregen_one_shot
     bool pregen;              // pool in use (philox refill, not disabled by flag)
     // host mirror (tmg_host_bind): the caller's page-locked arrays; p.h_* are their device-visible aliases
     int8_t* hm_board;
-    uint8_t *hm_mask, *hm_mask_bits, *hm_terminated;
+    uint8_t *hm_mask, *hm_mask_bits, *hm_terminated, *hm_board_packed;
     int32_t *hm_reward, *hm_moves_left;
     bool hm_bound;                  // any array bound: tmg_step_host then also reads page-locked actions in place
 };
@@ -141,12 +143,15 @@ static int launch_pregen(tmg_env* e, cudaStream_t st) {
     if (cudaStreamWaitEvent(e->side, e->ev_step, 0) != cudaSuccess) return TMG_ERR_CUDA;
     Params p = e->p;
     p.pool_tag = (int)(tag & 0x7fffffff);
+    p.pregen_one_shot = e->pregen_one_shot;
     const int rc = launch_by_shape(e, [&](auto shape) {
         typedef decltype(shape) S;
         constexpr int L = S::L;
         int grid = grid_for<L>(p.N);
-        if (grid > e->persistent_blocks) grid = e->persistent_blocks;
-        if (grid > e->pregen_grid_cap) grid = e->pregen_grid_cap;
+        if (!e->pregen_one_shot) {
+            if (grid > e->persistent_blocks) grid = e->persistent_blocks;
+            if (grid > e->pregen_grid_cap) grid = e->pregen_grid_cap;
+        }
         k_pregen<L, S::R, S::C><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), e->side>>>(p);
         return last_error();
     });
@@ -271,7 +276,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
                  o_pool_board = take((size_t)N * 2 * p.P), o_pool_mask = take((size_t)N * p.A),
                  o_pool_status = take((size_t)N * 4), o_mask_bits = take((size_t)N * ((p.A + 7) / 8)),
                  o_ctl = take((size_t)CTL_WORDS * 4), o_items = take((size_t)N * sizeof(uint2)),
-                 o_nsp = take((size_t)N);
+                 o_nsp = take((size_t)N), o_bpk = take((size_t)N * p.P);
     size_t req_cap = 1;   // requests of the launches in flight plus the batch being collected; an overwritten entry is harmless
     while (req_cap < (size_t)8 * N) req_cap <<= 1;
     const size_t o_ring = take(req_cap * sizeof(uint2));
@@ -303,6 +308,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     p.req_mask = (uint32_t)(req_cap - 1);
     p.n_special = reinterpret_cast<uint8_t*>(b + o_nsp);
     e->mask_bits_dev = reinterpret_cast<uint8_t*>(b + o_mask_bits);
+    e->board_packed_dev = reinterpret_cast<uint8_t*>(b + o_bpk);
     e->pregen = !p.use_inj && !(cfg->flags & TMG_FLAG_NO_PREGEN) && cfg->autoreset != TMG_AUTORESET_DISABLED;
     e->pregen_count = 0;
     e->waited_stream = nullptr;
@@ -315,7 +321,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     if (const char* pe = getenv("TMG_B200_PREGEN_EVERY")) { if (atoi(pe) > 0) e->pregen_every = atoi(pe); }
     for (int i = 0; i < tmg_env::RING; ++i) e->pregen_step[i] = 0;
     e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr; e->hm_terminated = nullptr;
-    e->hm_reward = nullptr; e->hm_moves_left = nullptr; e->hm_bound = false;
+    e->hm_reward = nullptr; e->hm_moves_left = nullptr; e->hm_bound = false; e->hm_board_packed = nullptr;
     p.req_ring = e->pregen ? reinterpret_cast<uint2*>(b + o_ring) : nullptr;
     e->persistent_blocks = prop.multiProcessorCount * TMG_STEP_MIN_BLOCKS;
     {
@@ -328,6 +334,7 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
         const char* capenv = getenv("TMG_B200_PREGEN_BLOCKS_PER_SM");
         const int per_sm = capenv ? atoi(capenv) : 0;
         e->pregen_grid_cap = per_sm > 0 ? prop.multiProcessorCount * per_sm : 0x7fffffff;
+        e->pregen_one_shot = getenv("TMG_B200_PREGEN_ONE_SHOT") != nullptr;
     }
     e->side = nullptr;
     bool ok = cudaMemset(p.episode, 0xff, (size_t)N * 4) == cudaSuccess &&       // -1: no board generated yet
@@ -383,6 +390,12 @@ static int refresh_mirror(tmg_env* e, cudaStream_t st) {
     const size_t N = (size_t)p.N;
     bool ok = true;
     if (e->hm_board) ok &= cudaMemcpyAsync(e->hm_board, p.board, N * 2 * p.P, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (e->hm_board_packed) {
+        const long long total = (long long)N * p.P;
+        k_pack_boards<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.board, e->board_packed_dev, (int)N, p.P);
+        ok &= cudaGetLastError() == cudaSuccess;
+        ok &= cudaMemcpyAsync(e->hm_board_packed, e->board_packed_dev, (size_t)total, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    }
     if (e->hm_mask) ok &= cudaMemcpyAsync(e->hm_mask, p.mask, N * p.A, cudaMemcpyDeviceToHost, st) == cudaSuccess;
     if (e->hm_mask_bits) {
         const int bpe = (p.A + 7) / 8;
@@ -402,10 +415,11 @@ int tmg_host_bind(tmg_env* e, const tmg_host_io* io, void* stream) {
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     static const tmg_host_io none = {};
     if (!io) io = &none;
-    void* host[6] = {io->board, io->mask, io->mask_bits, io->reward, io->terminated, io->num_moves_left};
-    void* dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* host[7] = {io->board, io->mask, io->mask_bits, io->reward, io->terminated, io->num_moves_left, io->board_packed};
+    void* dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (io->board_packed && e->p.K > 15) return TMG_ERR_INVALID_ARG;   // a colour must fit the low nibble
     bool any = false;
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < 7; ++i) {
         if (!host[i]) continue;
         if (reinterpret_cast<uintptr_t>(host[i]) % 16 != 0) return TMG_ERR_INVALID_ARG;
         // page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) memory only: the kernels access it directly
@@ -416,12 +430,14 @@ int tmg_host_bind(tmg_env* e, const tmg_host_io* io, void* stream) {
     e->hm_bound = any;
     e->hm_board = io->board; e->hm_mask = io->mask; e->hm_mask_bits = io->mask_bits;
     e->hm_reward = io->reward; e->hm_terminated = io->terminated; e->hm_moves_left = io->num_moves_left;
+    e->hm_board_packed = io->board_packed;
     e->p.h_board = static_cast<int8_t*>(dev[0]);
     e->p.h_mask = static_cast<uint8_t*>(dev[1]);
     e->p.h_mask_bits = static_cast<uint8_t*>(dev[2]);
     e->p.h_reward = static_cast<int32_t*>(dev[3]);
     e->p.h_terminated = static_cast<uint8_t*>(dev[4]);
     e->p.h_moves_left = static_cast<int32_t*>(dev[5]);
+    e->p.h_board_packed = static_cast<uint8_t*>(dev[6]);
     return refresh_mirror(e, st);
 }
 
@@ -546,8 +562,7 @@ static int onehot_launch(tmg_env* e, void* out, int elem_bytes, void* stream) {
     if (!e || !out) return TMG_ERR_INVALID_ARG;
     if (cudaSetDevice(e->cfg.device) != cudaSuccess) return TMG_ERR_CUDA;
     const Params p = e->p;
-    const long long total = (long long)p.N * e->planes * p.P;
-    const long long threads = (total + 3) / 4;
+    const long long threads = (long long)p.N * p.P;   // one thread per cell
     const int block = 256;
     const long long grid = (threads + block - 1) / block;
     if (grid > 0x7fffffffLL) return TMG_ERR_INVALID_ARG;
@@ -623,6 +638,13 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     };
     // arrays bound as the host mirror were already updated in place by the step kernel
     if (io->board != e->hm_board) back(io->board, p.board, N * 2 * p.P);
+    if (io->board_packed && io->board_packed != e->hm_board_packed) {
+        if (p.K > 15) return TMG_ERR_INVALID_ARG;
+        const long long total = (long long)N * p.P;
+        k_pack_boards<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.board, e->board_packed_dev, (int)N, p.P);
+        ok &= cudaGetLastError() == cudaSuccess;
+        back(io->board_packed, e->board_packed_dev, (size_t)total);
+    }
     if (io->reward != e->hm_reward) back(io->reward, p.reward, N * 4);
     if (io->terminated != e->hm_terminated) back(io->terminated, p.terminated, N);
     if (io->mask != e->hm_mask) back(io->mask, p.mask, N * p.A);
@@ -640,6 +662,13 @@ int tmg_step_host(tmg_env* e, const tmg_host_io* io, void* stream) {
     back(io->shuffled, p.shuffled, N);
     back(io->status, p.status, N * 4);
     if (!ok) return TMG_ERR_CUDA;
+    // The caller blocks on every step, so the wake-up latency of the wait is on the critical path: poll the stream for
+    // the usual length of a step before falling back to a blocking wait.
+    for (int spins = 0; spins < 200000; ++spins) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) return TMG_OK;
+        if (q != cudaErrorNotReady) { cudaGetLastError(); return TMG_ERR_CUDA; }
+    }
     return cudaStreamSynchronize(st) == cudaSuccess ? TMG_OK : TMG_ERR_CUDA;
 }
 

@@ -58,7 +58,7 @@ enum : uint32_t {
 };
 enum : uint32_t { SP_COOKIE = 1u, SP_VLASER = 2u, SP_HLASER = 4u, SP_BOMB = 8u };
 enum { AUTORESET_DISABLED = 0, AUTORESET_NEXT_STEP = 1, AUTORESET_SAME_STEP = 2 };
-enum : uint32_t { FLAG_NO_MASK = 1u, FLAG_NO_PREGEN = 2u, FLAG_BYTE_PLANES = 4u };
+enum : uint32_t { FLAG_NO_MASK = 1u, FLAG_NO_PREGEN = 2u, FLAG_BYTE_PLANES = 4u, FLAG_CONSTRUCTIVE_RESET = 8u };
 enum { OP_GRAVITY = 1, OP_REFILL, OP_RESOLVE_ROUND, OP_ACTIVATE, OP_COMBINE, OP_MOVE, OP_EFFECTIVE, OP_GENERATE,
        OP_SHUFFLE, OP_COUNT_LINES, OP_LINES, OP_LAST = OP_LINES, OP_BYTE_PLANES = 0x100 };
 enum { LINES_WORDS = 1 + 2 * 32 };   // OP_LINES output per env: n, then {info, cell set} per line (see RBoard::line_info)
@@ -103,11 +103,14 @@ struct Params {
     uint2* req_ring;         // [req_mask + 1] pool-refill requests {env, board number}, in request order (NULL: pool not in use).
                              // A request names the board it wants, so a late, repeated or overwritten entry is harmless.
     uint32_t req_mask;       // ring capacity - 1 (capacity = power of two >= 8 N)
+    int pregen_one_shot;     // k_pregen: a group generates ONE board and leaves (short-lived blocks: the block scheduler can then
+                             // give the SM slot to a step kernel of a higher-priority stream), instead of looping over the requests
     int commit_pregen;       // this launch closes a batch of requests: the next k_pregen launch serves [CTL_REQ_PREV, tail)
     int seq;                 // number of this tmg_step call: its parity selects the work-list counters
     // host mirror (tmg_host_bind): page-locked host arrays, as device-visible pointers, that the step kernel updates in
     // place over PCIe for exactly the envs whose board / mask changed (NULL = not bound)
     int8_t* h_board;         // [N][2][R][C]
+    uint8_t* h_board_packed; // [N][R][C]  colour | (type & 7) << 4: the same board in half the PCIe bytes (K <= 15)
     uint8_t* h_mask;         // [N][A]
     uint8_t* h_mask_bits;    // [N][(A+7)/8]  bit j of byte b = action 8b + j
     int32_t* h_reward;       // [N]  per-env scalars: k_gate writes them coalesced, the workers overwrite the reward of a move
@@ -478,6 +481,20 @@ template <int L, int RT = 0, int CT = 0> struct Board {
                 }
                 dst[b] = (uint8_t)v;
             }
+        }
+    }
+    // host mirror, packed form: one byte per cell, colour | (type & 7) << 4, from the byte planes at `src` (shared or global)
+    __device__ __forceinline__ void mirror_board_packed(const int8_t* src) {
+        uint8_t* dst = p.h_board_packed + (size_t)env * P;
+        if ((P & 3) == 0) {
+            const uint32_t* c4 = reinterpret_cast<const uint32_t*>(src);
+            const uint32_t* t4 = reinterpret_cast<const uint32_t*>(src + P);
+            uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll 1
+            for (int j = lane; j < (P >> 2); j += L) d4[j] = (c4[j] & 0x0f0f0f0fu) | ((t4[j] & 0x07070707u) << 4);
+        } else {
+#pragma unroll 1
+            for (int i = lane; i < P; i += L) dst[i] = (uint8_t)((src[i] & 15) | ((src[P + i] & 7) << 4));
         }
     }
     __device__ __forceinline__ void load_cursors() { dcur = p.draw_cursor[env]; scur = p.shuffle_cursor[env]; }
@@ -1713,6 +1730,59 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         elim_out = elim + n_new;                             // ref :378 (counters are uniform across lanes)
     }
 
+    // TMG_FLAG_CONSTRUCTIVE_RESET: board number `ep` of this env from a constructive line-free sampler instead of the
+    // reference's generate_board (whose redraw loop, ref :99-109, does not terminate for e.g. 32x32 / 7 colours).
+    // NOT the reference's algorithm; the contract (include/tmg_b200.h): cells in row-major
+    // order, each takes the next colour 1 + mulhi32(W, K) of stream 5 of the board (W = Philox(key, ctr = (k>>2, ep, env,
+    // 5))[k&3], k = 0, 1, ...) that does not complete a triple with the two cells to its left or the two above it (at most
+    // 64 draws per cell); a board without a possible move is drawn again from where the stream stands.  All lanes walk
+    // the cells together (the draws of a cell depend on the cells before it), each computing a Philox block of the window.
+    __device__ void generate_constructive(uint32_t ep, unsigned& effv, unsigned& effh) {
+        uint32_t cur = 0u, wbase = 0u;
+        bool have = false;
+        int attempts = 0;
+#pragma unroll 1
+        for (;;) {
+            sync();
+#pragma unroll 1
+            for (int i = lane; i < P; i += L) typ[i] = 1;
+#pragma unroll 1
+            for (int r = 0; r < R; ++r) {
+                sync();                                      // the rows above are visible
+                int l1 = -1, l2 = -2;
+#pragma unroll 1
+                for (int c = 0; c < C; ++c) {
+                    const int u1 = r >= 2 ? (int)col[(r - 1) * C + c] : -1, u2 = r >= 2 ? (int)col[(r - 2) * C + c] : -2;
+                    const int forbid_v = (u1 == u2) ? u1 : -1, forbid_h = (c >= 2 && l1 == l2) ? l1 : -1;
+                    int k = 1;
+#pragma unroll 1
+                    for (int tries = 0;; ++tries) {
+                        if (!have || cur - wbase >= (uint32_t)(4 * L)) {      // next window of the stream: one block per lane
+                            sync();
+                            wbase = cur & ~3u;
+                            uint32_t w[4];
+                            philox4x32_10((wbase >> 2) + (uint32_t)lane, ep, gid, 5u, p.key0, p.key1, w);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) s.wbuf[4 * lane + q] = w[q];
+                            have = true;
+                            sync();
+                        }
+                        k = 1 + (int)__umulhi(s.wbuf[cur - wbase], (uint32_t)K);
+                        ++cur;
+                        if (k != forbid_v && k != forbid_h) break;
+                        if (tries >= 63) { status |= ST_RESET_CAP; break; }   // (K <= 2: a line-free colour may not exist)
+                    }
+                    if (lane == 0) col[r * C + c] = (int8_t)k;
+                    l2 = l1; l1 = k;
+                }
+            }
+            sync();
+            const bool any = mask_bits(effv, effh);          // possible_move (ref :558-569)
+            if (any) break;
+            if (++attempts >= p.max_iters) { status |= ST_RESET_CAP; break; }
+        }
+    }
+
     // generate_board (ref :95-112) for board number `ep` of this env: a pure function of (seed, env, ep)
     __device__ __forceinline__ void begin_generate(uint32_t ep) {
         episode = ep;
@@ -1841,10 +1911,7 @@ __device__ __forceinline__ uint32_t ctl_read(uint32_t* w) { return atomicAdd(w, 
 // Called once by every warp (k_gate) / group (k_reset) of a launch after its appends.  The last caller records the
 // range of refill requests this launch issued under its tag and, for a step, clears the other parity's work counters
 // for the next step.  Stream order makes all of it visible to the launches that follow.
-__device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers, bool is_step) {
-    __threadfence();
-    if (atomicAdd(&p.ctl[CTL_DONE], 1u) != callers - 1u) return;
-    __threadfence();
+__device__ __forceinline__ void launch_bookkeeping(const Params& p, bool is_step) {
     if (p.commit_pregen) {   // the host launches k_pregen `pool_tag` after this launch: it serves the requests since the last batch
         const uint32_t tail = ctl_read(&p.ctl[CTL_REQ_TAIL]), prev = p.ctl[CTL_REQ_PREV];
         const int slot = p.pool_tag % PG_RING;
@@ -1860,6 +1927,12 @@ __device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers,
         p.ctl[CTL_WL_COUNT_LO + nq] = 0u;
         p.ctl[CTL_WL_HEAD + nq] = 0u;
     }
+}
+__device__ __forceinline__ void commit_launch(const Params& p, uint32_t callers, bool is_step) {
+    __threadfence();
+    if (atomicAdd(&p.ctl[CTL_DONE], 1u) != callers - 1u) return;
+    __threadfence();
+    launch_bookkeeping(p, is_step);
     p.ctl[CTL_DONE] = 0u;
 }
 __device__ __forceinline__ void action_to_cells(int a, int R, int C, int& i1, int& i2) {  // ref :80-91
@@ -1887,7 +1960,9 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         } else {
             const int ep = p.episode[gc.env] + 1;    // generate_board (ref board.py:95-112)
             b.sync();
-            if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
+            if (p.flags & FLAG_CONSTRUCTIVE_RESET) {
+                b.generate_constructive((uint32_t)ep, effv, effh);
+            } else if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
                 int iters = 0;                       // line removal on packed rows, as in k_pregen
                 bool capped = false;
                 if (p.K <= 4) b.template generate_packed<2>((uint32_t)ep, iters, capped);
@@ -1925,9 +2000,11 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
 #define TMG_GATE_EPT 2   // measured on B200 (65 536 envs): 1 and 2 envs per thread 371-373 M steps/s, 4 envs per thread 362 M
 #endif
 enum { GATE_EPT = TMG_GATE_EPT };   // envs per thread of k_gate: four independent chains of dependent loads per thread, a quarter of the atomics
-__global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) {
-    const int wl = (int)threadIdx.x & 31;
-    const int env0 = ((int)blockIdx.x * 4 + ((int)threadIdx.x >> 5)) * (32 * GATE_EPT) + wl;   // this thread: env0 + 32 k
+// the envs [chunk * 32 GATE_EPT, (chunk + 1) * 32 GATE_EPT) by one warp (lane wl takes env0 + 32 k).
+// (Gating inside the persistent step kernel -- a phase of k_work with a counter barrier behind it -- was built and measured
+// SLOWER than this separate launch: 0.190 vs 0.171 ms per 65 536-env step; see DESIGN.md.)
+__device__ __forceinline__ void gate_chunk(const Params& p, int chunk, int wl) {
+    const int env0 = chunk * (32 * GATE_EPT) + wl;
     const int q = p.seq & 1;
     bool heavy[GATE_EPT], hi[GATE_EPT], req[GATE_EPT];
     uint32_t packed[GATE_EPT], req_ep[GATE_EPT];
@@ -2023,6 +2100,10 @@ __global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) 
         hbase += (uint32_t)__popc(hm[k]); lbase += (uint32_t)__popc(lm[k]); rbase += (uint32_t)__popc(rm[k]);
     }
     __syncwarp(0xffffffffu);
+}
+__global__ void __launch_bounds__(128) k_gate(const __grid_constant__ Params p) {
+    const int wl = (int)threadIdx.x & 31;
+    gate_chunk(p, (int)blockIdx.x * 4 + ((int)threadIdx.x >> 5), wl);
     if (wl == 0) commit_launch(p, gridDim.x * (blockDim.x >> 5), true);
 }
 
@@ -2072,6 +2153,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
             clean = true; all_normal = false;
         } else {
             if (!inline_gen) continue;
+            if (p.flags & FLAG_CONSTRUCTIVE_RESET) { b.generate_constructive((uint32_t)next_ep, effv, effh); continue; }
             b.begin_generate((uint32_t)next_ep);
             clean = false; all_normal = true;
         }
@@ -2086,6 +2168,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
         b.status |= p.pool_status[env];
         if (eff) b.store_cursors();
         if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, p.board_vecw);
+        if (p.h_board_packed) b.mirror_board_packed(p.pool_board + (size_t)env * 2 * p.P);
         if (want_mask && (p.h_mask || p.h_mask_bits)) {
             b.copy_mask(b.s.mask, p.pool_mask + (size_t)env * p.A);
             b.sync();
@@ -2095,6 +2178,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
         if (dirty) {
             b.store_board(); b.store_cursors();
             if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, b.s.board, p.board_vecw);
+            if (p.h_board_packed) b.mirror_board_packed(b.s.board);
         }
         if (want_mask) {
             if (zero_mask) { b.store_zero_mask(); b.mirror_mask(true); }
@@ -2282,6 +2366,8 @@ template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg
                         b.sync();
                         b.mask_bits(effv, effh);
                         pool_used = true;
+                    } else if (p.flags & FLAG_CONSTRUCTIVE_RESET) {
+                        b.generate_constructive((uint32_t)episode, effv, effh);
                     } else {
                         b.begin_generate((uint32_t)episode);                       // ref board.py:95-112
                         b.playability(false, true, effv, effh);
@@ -2303,6 +2389,7 @@ template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg
             else if (touched) { b.mask_to_smem(effv, effh); b.store_mask(); }
         }
         if (p.h_board && touched) b.copy_board(p.h_board + (size_t)env * 2 * p.P, b.s.board, p.board_vecw);
+        if (p.h_board_packed && touched) b.mirror_board_packed(b.s.board);
         if (want_mask && p.T > 0 && (terminal || touched)) b.mirror_mask(terminal);
         merge_status(b, p);
         if (touched) {
@@ -2339,6 +2426,8 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
     const uint32_t start = p.ctl[CTL_PG_RANGE + 2 * slot], n = p.ctl[CTL_PG_RANGE + 2 * slot + 1] - start;
     Board<L, RT, CT> b(group_smem<L>(gc.g), p, gc.lane, gc.gmask, gc.gshift, 0);
     bool have = false, done = false, capped = false, staged = false;   // staged: the line-free board is already in shared memory
+    bool masked = false;                                                // ... and so are its mask bits (cv, ch)
+    unsigned cv = 0u, ch = 0u;
     int from = 0, iters = 0, ep = 0;
 #pragma unroll 1
     for (;;) {
@@ -2357,7 +2446,10 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
                     b.sync();
                     capped = false; from = b.R - 1; iters = 0; have = true;
                     staged = false;
-                    if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
+                    if (p.flags & FLAG_CONSTRUCTIVE_RESET) {
+                        b.generate_constructive((uint32_t)ep, cv, ch);
+                        staged = true; masked = true;
+                    } else if (Board<L, RT, CT>::PACKED_GEN && !p.use_inj && p.K <= 8 && CT * (p.K <= 4 ? 2 : 3) <= 32) {
                         // fixed small shapes: the whole line removal on packed rows, then straight to the finish
                         if (p.K <= 4) b.template generate_packed<2>((uint32_t)ep, iters, capped);
                         else b.template generate_packed<3>((uint32_t)ep, iters, capped);
@@ -2371,8 +2463,9 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         if (!have) continue;
         if (!staged && b.redraw_iteration(from, iters, capped)) continue;   // ref :99-101, one iteration
         // line-free: possible_move / shuffle (ref :102-109, rare) and the mask, then publish the pool entry
-        unsigned effv = 0u, effh = 0u;
-        if (capped) b.mask_bits(effv, effh);
+        unsigned effv = cv, effh = ch;
+        if (masked) masked = false;                            // the constructive generator left the mask of its board
+        else if (capped) b.mask_bits(effv, effh);
         else b.playability(true, true, effv, effh, iters);
         b.end_generate();
         b.sync();
@@ -2390,6 +2483,7 @@ template <int L, int RT, int CT> __global__ void __launch_bounds__(Cfg<L>::THREA
         if (gc.lane == 0) p.pool_episode[env] = ep;
         b.sync();
         have = false;
+        if (p.pregen_one_shot) done = true;
     }
 }
 
@@ -2552,9 +2646,12 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
             unsigned v, h;
             const int ep = p.episode[env] + 1;
             b.sync();
-            b.begin_generate((uint32_t)ep);
-            b.playability(false, true, v, h);
-            b.end_generate();
+            if (p.flags & FLAG_CONSTRUCTIVE_RESET) b.generate_constructive((uint32_t)ep, v, h);
+            else {
+                b.begin_generate((uint32_t)ep);
+                b.playability(false, true, v, h);
+                b.end_generate();
+            }
             if (lane == 0) p.episode[env] = ep;
             break;
         }
@@ -2586,45 +2683,24 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
     }
 }
 
-// OneHotWrapper._one_hot_encode_board (ref wrappers.py:54-69).  One thread per 4 output bytes (or 1 float4).
+// OneHotWrapper._one_hot_encode_board (ref wrappers.py:54-69).  One thread per cell: two coalesced byte loads, then one
+// store per output plane -- a warp writes 32 consecutive elements of a plane row per store.  HBM-bound: 2P bytes in,
+// (K + S) P elements out per env.
 template <typename OUT> __global__ void __launch_bounds__(256) k_onehot(const Params p, OUT* __restrict__ out, int planes) {
-    const long long total = (long long)p.N * planes * p.P;
-    const long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (q0 >= total) return;
-    const int pp = planes * p.P;
-    OUT v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const long long q = q0 + j;
-        OUT o = (OUT)0;
-        if (q < total) {
-            const int env = (int)(q / pp);
-            const int rem = (int)(q - (long long)env * pp);
-            const int plane = rem / p.P, cell = rem - plane * p.P;
-            const int8_t* bd = p.board + (size_t)env * 2 * p.P;
-            if (plane < p.K) o = (OUT)(bd[cell] == plane + 1);
-            else {  // enabled specials in the order cookie(-1), v(2), h(3), bomb(4) (ref wrappers.py:40-46)
-                int idx = plane - p.K, want = 99;
-                if (p.specials & SP_COOKIE) { if (idx == 0) want = -1; --idx; }
-                if (p.specials & SP_VLASER) { if (idx == 0) want = 2; --idx; }
-                if (p.specials & SP_HLASER) { if (idx == 0) want = 3; --idx; }
-                if (p.specials & SP_BOMB) { if (idx == 0) want = 4; --idx; }
-                o = (OUT)(bd[p.P + cell] == want);
-            }
-        }
-        v[j] = o;
-    }
-    if (q0 + 3 < total) {
-        if (sizeof(OUT) == 1) {
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(out) + q0) =
-                (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[q0 + j] = v[j];
-        }
-    } else {
-        for (int j = 0; j < 4 && q0 + j < total; ++j) out[q0 + j] = v[j];
-    }
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (long long)p.N * p.P) return;
+    const int env = (int)(q / p.P), cell = (int)(q - (long long)env * p.P);
+    const int8_t* bd = p.board + (size_t)env * 2 * p.P;
+    const int colour = bd[cell], type = bd[p.P + cell];
+    OUT* o = out + (size_t)env * planes * p.P + cell;
+#pragma unroll 4
+    for (int k = 0; k < p.K; ++k) o[(size_t)k * p.P] = (OUT)(colour == k + 1);
+    o += (size_t)p.K * p.P;
+    // enabled specials in the order cookie(-1), v(2), h(3), bomb(4) (ref wrappers.py:40-46)
+    if (p.specials & SP_COOKIE) { *o = (OUT)(type == -1); o += p.P; }
+    if (p.specials & SP_VLASER) { *o = (OUT)(type == 2); o += p.P; }
+    if (p.specials & SP_HLASER) { *o = (OUT)(type == 3); o += p.P; }
+    if (p.specials & SP_BOMB) { *o = (OUT)(type == 4); o += p.P; }
 }
 
 // legal-move mask as bits for the host-buffer path: out[env][b] bit j = mask[env][8b + j]  (one thread per output byte)
@@ -2649,6 +2725,15 @@ __global__ void k_commit_batch(const __grid_constant__ Params p) {
     p.ctl[CTL_PG_RANGE + 2 * slot + 1] = tail;
     p.ctl[CTL_PG_HEAD + slot] = 0u;
     p.ctl[CTL_REQ_PREV] = tail;
+}
+
+// the packed form of every board (full refresh of a bound packed host mirror): one thread per 4 cells
+__global__ void __launch_bounds__(256) k_pack_boards(const int8_t* __restrict__ board, uint8_t* __restrict__ out, int n_envs, int P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_envs * P) return;
+    const int env = (int)(i / P), cell = (int)(i - (long long)env * P);
+    const int8_t* b = board + (size_t)env * 2 * P;
+    out[i] = (uint8_t)((b[cell] & 15) | ((b[P + cell] & 7) << 4));
 }
 
 __global__ void k_clear_status(uint32_t* st, int n) {

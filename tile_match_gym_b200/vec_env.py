@@ -55,6 +55,9 @@ class TileMatchVecEnv:
                       or "onehot" (OneHotWrapper planes, uint8)
       copy_outputs    step() returns fresh copies of reward / terminated / the info tensors instead of views of the
                       engine's buffers (see step(): the views are overwritten in place by the next call)
+      constructive_reset  NOT reference behaviour: boards come from the constructive line-free sampler of
+                      TMG_FLAG_CONSTRUCTIVE_RESET (include/tmg_b200.h) instead of generate_board -- for shapes such as
+                      32x32 / 7 colours, where the reference's generate_board never returns
       byte_planes     diagnostics: run the moves on the shared-memory byte-plane engine (TMG_FLAG_BYTE_PLANES) instead of
                       the register-resident bit-plane engine; results are identical
     """
@@ -66,7 +69,7 @@ class TileMatchVecEnv:
                  autoreset: str = "next_step", refill: str = "philox", env_id_offset: int = 0,
                  compute_mask: bool = True, obs: str = "int8", max_reset_iters: int = 0,
                  render_mode: str = "string", pregenerate: bool = True, copy_outputs: bool = False,
-                 byte_planes: bool = False):
+                 byte_planes: bool = False, constructive_reset: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("tile_match_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self._lib = nat.lib()
@@ -103,7 +106,8 @@ class TileMatchVecEnv:
                          self.num_colours, self.num_moves, self.specials, nat.AUTORESET[autoreset],
                          nat.REFILL[refill],
                          (0 if compute_mask else nat.FLAG_NO_MASK) | (0 if pregenerate else nat.FLAG_NO_PREGEN)
-                         | (nat.FLAG_BYTE_PLANES if byte_planes else 0),
+                         | (nat.FLAG_BYTE_PLANES if byte_planes else 0)
+                         | (nat.FLAG_CONSTRUCTIVE_RESET if constructive_reset else 0),
                          int(max_reset_iters),
                          self.seed & 0xFFFFFFFFFFFFFFFF, self.env_id_offset)
         h = C.c_void_p()
@@ -441,6 +445,7 @@ class HostStepper:
         shapes = {"actions": ((N,), torch.int32), "board": ((N, 2, R, Cc), torch.int8), "reward": ((N,), torch.int32),
                   "terminated": ((N,), torch.uint8), "mask": ((N, A), torch.uint8),
                   "mask_bits": ((N, (A + 7) // 8), torch.uint8), "num_moves_left": ((N,), torch.int32),
+                  "board_packed": ((N, R, Cc), torch.uint8),
                   "is_combination_match": ((N,), torch.uint8), "num_new_specials": ((N,), torch.int32),
                   "num_specials_activated": ((N,), torch.int32), "shuffled": ((N,), torch.uint8),
                   "status": ((N,), torch.int32)}
@@ -460,7 +465,7 @@ class HostStepper:
             # the env owns the bound arrays from here on: the kernels of ANY later step write into them, whether or not
             # this object is still alive (they are released by close() / env.unbind_host_mirror() / env.close())
             env._mirror_keep = self.host
-            self._mirrored = [n for n in ("board", "mask", "mask_bits") if n in self.host]
+            self._mirrored = [n for n in ("board", "board_packed", "mask", "mask_bits") if n in self.host]
             scalars = [n for n in ("reward", "terminated", "num_moves_left") if n in self.host]
             # per step over PCIe: the mirrored scalars of every env + one entry of every mirrored array per env that
             # changed + whatever else is copied in full
@@ -481,6 +486,16 @@ class HostStepper:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+    def board(self) -> np.ndarray:
+        """The boards as the reference's (N, 2, R, C) int8 planes, from whichever board form was copied back: `board`, or
+        `board_packed` (one byte per cell: colour | (type & 7) << 4, cookie type -1 stored as 7)."""
+        if "board" in self.host:
+            return self.host["board"].numpy()
+        pk = self.host["board_packed"].numpy()
+        typ = (pk >> 4).astype(np.int8)
+        typ[typ == 7] = -1
+        return np.stack([(pk & 15).astype(np.int8), typ], axis=1)
 
     def effective_actions(self, i: int):
         """The reference's info["effective_actions"] list of env i from whichever mask form was copied back."""
