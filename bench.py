@@ -278,6 +278,7 @@ def main():
     ap.add_argument("--num-moves", type=int, default=0, help="diagnostic: episode length (huge = no resets)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-rollout", action="store_true")
+    ap.add_argument("--skip-no-reset", action="store_true")
     ap.add_argument("--step-stream-priority", type=int, default=0,
                     help="diagnostic: run the steps on a CUDA stream of this priority (-1 = above the library's side stream)")
     ap.add_argument("--byte-planes", action="store_true", help="diagnostic: TMG_FLAG_BYTE_PLANES (shared-memory byte-plane engine)")
@@ -389,7 +390,7 @@ def main():
 
     # the same steps with no episode end inside the run ("with and without autoreset cost")
     no_reset_ms = None
-    if not inject and not args.num_moves:
+    if not inject and not args.num_moves and not args.skip_no_reset:
         env_nr = make_env(1 << 20)
         s_nr = min(args.steps, 40)
         ms_nr, _, _ = timed_steps(env_nr, s_nr, max(5, min(args.warmup, 20)), 1 << 20)

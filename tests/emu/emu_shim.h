@@ -61,6 +61,11 @@ using std::max;
 using std::min;
 
 static inline void __syncwarp(unsigned mask) { emu::gather(0, mask); }
+static inline int __any_sync(unsigned mask, int pred) {
+    const uint64_t* v = emu::gather(pred ? 1 : 0, mask);
+    for (int i = 0; i < 32; ++i) if (((mask >> i) & 1u) && v[i]) return 1;
+    return 0;
+}
 static inline unsigned __ballot_sync(unsigned mask, int pred) {
     const uint64_t* v = emu::gather(pred ? 1 : 0, mask);
     unsigned out = 0;

@@ -2412,6 +2412,10 @@ template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg
     if (lane == 0) commit_launch(p, gridDim.x * (uint32_t)Cfg<L>::GPB, false);
 }
 
+// (Two boards per warp -- half a warp holds the <= 16 packed rows of a board, one instruction stream serves both -- was
+// built and measured SLOWER on B200: 340 M vs 368 M steps/s at 65 536 envs, 691 M vs 706 M at 1 M.  A redraw of n rows needs
+// 10 n / 4 Philox blocks, which is 40 % of an iteration; two redraws together overflow the warp's 32 lanes and take two
+// passes, so nothing is shared there, and the bookkeeping of two boards costs more than the rest saves.)
 // Pool refill: generate_board (ref board.py:95-112) of the next board of every env whose request this launch serves.
 // Runs on a side stream, off the step path; touches no env state.  The fixed small shapes remove the lines on packed
 // rows (Board::generate_packed); the others run the byte-plane loop, one scan + redraw iteration per trip.
