@@ -1,7 +1,7 @@
 """Diagnostics: joins an ncu source-page CSV (SASS view) of one kernel with `nvdisasm -g -c` line info and prints where the
 samples, executed instructions and no-instruction stalls are, per source function (several source files) and per line.
 Usage: python scripts/ncu_by_function.py <src.csv from `ncu -i rep --page source --csv`> <nvdisasm -g -c output of the cubin>
-       <mangled kernel name> [top lines]"""
+       <mangled kernel name> [top lines] [substring of the kernel name in the report]"""
 import csv
 import re
 import sys
@@ -27,6 +27,17 @@ for ln in open(sass):
     if m:
         addr_line[int(m.group(1), 16)] = cur
 rows = list(csv.reader(open(src_csv)))
+# a report with several kernels repeats {"Kernel Name", name} + header: keep the sections of the wanted kernel only
+want = sys.argv[5] if len(sys.argv) > 5 else None
+if want:
+    keep, on = rows[:2], False
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            on = want in r[1]
+            continue
+        if on and not (r and r[0] == "Address"):
+            keep.append(r)
+    rows = keep
 hdr = rows[1]
 ia, isamp, iex = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 inoi = hdr.index("stall_no_inst") if "stall_no_inst" in hdr else None
