@@ -108,7 +108,7 @@ static void run_group(int L, int first_tid, void (*fn)()) {
 using namespace tmg;
 
 static Params g_params;
-static bool rbk() { return rb_supported(32, g_params.R, g_params.K, g_params.flags); }
+static bool rbk() { return rb_supported(32, g_params.R, g_params.K, g_params.flags, g_params.use_inj); }
 template <int L> static void e_reset() {
     if (g_params.R == 10 && g_params.C == 10 && L == 32) k_reset<32, 10, 10>(g_params);
     else if (g_params.R == 9 && g_params.C == 9 && L == 32) k_reset<32, 9, 9>(g_params);

@@ -483,7 +483,7 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
         int grid = grid_for<L>(p.N);
         if (grid > e->persistent_blocks) grid = e->persistent_blocks;
         if constexpr (UsesRB<L, S::R>::maybe) {   // the register-resident engine where it applies (tmg_rb.cuh)
-            if (rb_supported(L, p.R, p.K, p.flags)) {
+            if (rb_supported(L, p.R, p.K, p.flags, p.use_inj)) {
                 k_work<L, S::R, S::C, true><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
                 return last_error();
             }
@@ -521,7 +521,7 @@ static int rollout(tmg_env* e, int policy, const int32_t* actions_dev, int32_t n
         int grid = grid_for<L>(p.N);
         if (grid > e->persistent_blocks) grid = e->persistent_blocks;
         if constexpr (UsesRB<L, S::R>::maybe) {   // the register-resident engine where it applies (tmg_rb.cuh)
-            if (rb_supported(L, p.R, p.K, p.flags)) {
+            if (rb_supported(L, p.R, p.K, p.flags, p.use_inj)) {
                 k_rollout<L, S::R, S::C, true><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
                 return last_error();
             }

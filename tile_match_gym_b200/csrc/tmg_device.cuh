@@ -33,15 +33,15 @@
 #define TMG_SITE_HERE
 #endif
 
-// Code-size knobs.  The step kernel is bound by instruction supply (ncu: stall_no_instruction is the top stall, L1.5
-// hit rate 67 %), but rolling the row loops (-DTMG_UNROLL_ROWS=1 -DTMG_UNROLL_PHILOX=1 -DTMG_FUSED_FALL=0: 15 % less
-// SASS) measured 10 % SLOWER on B200 than the unrolled form: the extra executed instructions cost more than the
-// cache misses they save.
+// Code-size knobs.  The step kernels are bound by instruction supply (ncu: stall_no_instruction is the top stall).  In
+// round 1 rolling these loops measured 10 % SLOWER (more executed instructions); with the register-resident engine of
+// round 2 the balance flipped: Philox rolled by 2 and the byte-plane row loops rolled measured +7 % at 65 536 envs and +8 %
+// at 1 M (see tmg_rb.cuh for the whole ladder).
 #ifndef TMG_UNROLL_PHILOX
-#define TMG_UNROLL_PHILOX 10
+#define TMG_UNROLL_PHILOX 2
 #endif
 #ifndef TMG_UNROLL_ROWS
-#define TMG_UNROLL_ROWS 32
+#define TMG_UNROLL_ROWS 1
 #endif
 #ifndef TMG_FUSED_FALL
 #define TMG_FUSED_FALL 1
@@ -364,6 +364,17 @@ __device__ __noinline__ SlowOut slow_round(GroupSmem<L>* sm, const Params* pp, i
 template <int L, int RT, int CT>
 __device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift,
                                                  int env, int i1, int i2);
+// the cold ends of a work-list item: playability of a moved board whose mask is not known (shuffle / literal rule) and
+// generate_board inside the step -- out of line so that the step kernel's hot code stays small (it is bound by instruction
+// supply: every KB of inlined cold code that was removed from it measured as throughput)
+struct FinishOut { unsigned effv, effh; uint32_t status; int shuffled; uint64_t dcur, scur; unsigned last_S; };
+// host-mirror write-through of one env (tmg_host_bind) and the all-zero mask of a terminal step: out of line as well
+enum { MIRROR_BOARD_SMEM = 1, MIRROR_BOARD_POOL = 2, MIRROR_MASK_SMEM = 4, MIRROR_MASK_POOL = 8, MIRROR_MASK_ZERO = 16, STORE_ZERO_MASK = 32 };
+template <int L, int RT, int CT>
+__device__ __noinline__ void mirror_item(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env, int what);
+template <int L, int RT, int CT>
+__device__ __noinline__ FinishOut slow_finish(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env,
+                                              int do_playability, int do_generate, int next_ep, uint64_t dcur, uint64_t scur);
 
 // RT/CT > 0 fix the board shape at compile time (full unrolling, immediate shared-memory offsets); 0 = runtime shape.
 template <int L, int RT = 0, int CT = 0> struct Board {
@@ -1816,6 +1827,45 @@ __device__ __noinline__ SlowOut slow_round(GroupSmem<L>* sm, const Params* pp, i
     return o;
 }
 template <int L, int RT, int CT>
+__device__ __noinline__ void mirror_item(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env, int what) {
+    Board<L, RT, CT> b(*sm, *pp, lane, gmask, gshift, env);
+    const Params& p = *pp;
+    b.sync();
+    if (what & STORE_ZERO_MASK) b.store_zero_mask();
+    if (what & (MIRROR_BOARD_SMEM | MIRROR_BOARD_POOL)) {
+        const int8_t* src = (what & MIRROR_BOARD_POOL) ? p.pool_board + (size_t)env * 2 * p.P : b.s.board;
+        if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, src, p.board_vecw);
+        if (p.h_board_packed) b.mirror_board_packed(src);
+    }
+    if (p.h_mask || p.h_mask_bits) {
+        if (what & MIRROR_MASK_POOL) {
+            b.copy_mask(b.s.mask, p.pool_mask + (size_t)env * p.A);
+            b.sync();
+            b.mirror_mask(false);
+        } else if (what & MIRROR_MASK_SMEM) b.mirror_mask(false);
+        else if (what & MIRROR_MASK_ZERO) b.mirror_mask(true);
+    }
+}
+template <int L, int RT, int CT>
+__device__ __noinline__ FinishOut slow_finish(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift, int env,
+                                              int do_playability, int do_generate, int next_ep, uint64_t dcur, uint64_t scur) {
+    Board<L, RT, CT> b(*sm, *pp, lane, gmask, gshift, env);
+    b.dcur = dcur; b.scur = scur;
+    FinishOut o;
+    o.effv = 0u; o.effh = 0u; o.shuffled = 0;
+    if (do_playability) o.shuffled = b.playability(true, false, o.effv, o.effh);           // ref board.py:381-391
+    if (do_generate) {                                                                     // ref board.py:95-112 for board `next_ep`
+        if (pp->flags & FLAG_CONSTRUCTIVE_RESET) b.generate_constructive((uint32_t)next_ep, o.effv, o.effh);
+        else {
+            b.begin_generate((uint32_t)next_ep);
+            b.playability(false, true, o.effv, o.effh);
+            b.end_generate();
+        }
+    }
+    o.status = b.status; o.dcur = b.dcur; o.scur = b.scur; o.last_S = b.last_S;
+    return o;
+}
+template <int L, int RT, int CT>
 __device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params* pp, int lane, unsigned gmask, int gshift,
                                                  int env, int i1, int i2) {
     Board<L, RT, CT> b(*sm, *pp, lane, gmask, gshift, env);
@@ -1832,14 +1882,14 @@ __device__ __noinline__ SlowOut slow_combination(GroupSmem<L>* sm, const Params*
 // The step kernels take the choice as a template argument (RBK), made by the host with rb_supported(): an instantiation
 // carries the move code of one engine only.
 template <int L, int RT> struct UsesRB { static constexpr bool maybe = L == 32 && RT <= 10; };
-__host__ __device__ inline bool rb_supported(int lanes, int R, int K, uint32_t flags) {
-    return lanes == 32 && R <= 10 && K <= 7 && !(flags & FLAG_BYTE_PLANES);
+__host__ __device__ inline bool rb_supported(int lanes, int R, int K, uint32_t flags, int use_inj) {
+    return lanes == 32 && R <= 10 && K <= 7 && !(flags & FLAG_BYTE_PLANES) && !use_inj;   // (injected refill: byte planes)
 }
 // A move on the register-resident engine for a Board whose byte planes are staged in shared memory: pack, move, mask,
 // unpack.  Returns the eliminations (without num_new_specials); mask_ok <- effv / effh are the mask of the final board
 // and a move is possible (otherwise the caller runs Board::playability on the byte planes: shuffle / literal rule).
-template <int RT, int CT, typename B>
-__device__ __forceinline__ int rb_move(RBoard<RT, CT>& rb, B& b, int i1, int i2, int& is_comb, unsigned& effv, unsigned& effh, bool& mask_ok) {
+template <int RT, int CT, bool INJ, typename B>
+__device__ __forceinline__ int rb_move(RBoard<RT, CT, INJ>& rb, B& b, int i1, int i2, int& is_comb, unsigned& effv, unsigned& effh, bool& mask_ok) {
     rb.dcur = b.dcur;
     rb.status = 0u;
     rb.pack_from_smem();
@@ -2144,47 +2194,34 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
     const int next_ep = regenerate ? p.episode[env] + 1 : 0;
     const bool inline_gen = regenerate && !from_pool;
     const bool dirty = eff || inline_gen;
-    // phase 0: playability of the moved board; phase 1: generate_board of the next episode.  One call site.
-#pragma unroll 1
-    for (int phase = 0; phase < 2; ++phase) {
-        bool clean, all_normal;
-        if (phase == 0) {
-            if (!eff || mask_ok) continue;
-            clean = true; all_normal = false;
-        } else {
-            if (!inline_gen) continue;
-            if (p.flags & FLAG_CONSTRUCTIVE_RESET) { b.generate_constructive((uint32_t)next_ep, effv, effh); continue; }
-            b.begin_generate((uint32_t)next_ep);
-            clean = false; all_normal = true;
-        }
-        const bool sh = b.playability(clean, all_normal, effv, effh);      // ref board.py:381-391 / :99-109
-        if (phase == 0) shuffled = sh;
-        else b.end_generate();
+    // playability of the moved board (only when its mask is not known yet) and generate_board of the next episode when
+    // the pool does not hold it: both rare, both out of line
+    if ((eff && !mask_ok) || inline_gen) {
+        b.sync();
+        const FinishOut fo = slow_finish<L, RT, CT>(&b.s, &p, lane, b.gmask, b.gshift, env, eff && !mask_ok, inline_gen, next_ep, b.dcur, b.scur);
+        effv = fo.effv; effh = fo.effh; shuffled = fo.shuffled;
+        b.status |= fo.status; b.dcur = fo.dcur; b.scur = fo.scur; b.last_S = fo.last_S;
     }
+    const bool mirrored = p.h_board || p.h_board_packed || p.h_mask || p.h_mask_bits;
+    int mirror = 0;
     if (from_pool) {                       // board and mask of the new episode come straight from the pool
         b.sync();
         b.copy_board(p.board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, p.board_vecw);
         if (want_mask) b.copy_mask(p.mask + (size_t)env * p.A, p.pool_mask + (size_t)env * p.A);
         b.status |= p.pool_status[env];
         if (eff) b.store_cursors();
-        if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, p.pool_board + (size_t)env * 2 * p.P, p.board_vecw);
-        if (p.h_board_packed) b.mirror_board_packed(p.pool_board + (size_t)env * 2 * p.P);
-        if (want_mask && (p.h_mask || p.h_mask_bits)) {
-            b.copy_mask(b.s.mask, p.pool_mask + (size_t)env * p.A);
-            b.sync();
-            b.mirror_mask(false);
-        }
+        mirror = MIRROR_BOARD_POOL | (want_mask ? MIRROR_MASK_POOL : 0);
     } else {
         if (dirty) {
             b.store_board(); b.store_cursors();
-            if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, b.s.board, p.board_vecw);
-            if (p.h_board_packed) b.mirror_board_packed(b.s.board);
+            mirror = MIRROR_BOARD_SMEM;
         }
         if (want_mask) {
-            if (zero_mask) { b.store_zero_mask(); b.mirror_mask(true); }
-            else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); b.mirror_mask(false); }
+            if (zero_mask) mirror |= STORE_ZERO_MASK | MIRROR_MASK_ZERO;
+            else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); mirror |= MIRROR_MASK_SMEM; }
         }
     }
+    if ((mirrored && mirror) || (mirror & STORE_ZERO_MASK)) mirror_item<L, RT, CT>(&b.s, &p, lane, b.gmask, b.gshift, env, mirror);
     merge_status(b, p);
     if (dirty || from_pool) {              // scheduling hint for the next step: special tiles on the board (a fresh board has none)
         const int nsp = regenerate ? 0 : min(255, b.radd(__popc(b.last_S)));
@@ -2527,8 +2564,8 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
     if constexpr (L == 32) {
         const bool rb_op = op == OP_GRAVITY || op == OP_RESOLVE_ROUND || op == OP_ACTIVATE || op == OP_COMBINE || op == OP_MOVE ||
                            op == OP_COUNT_LINES || op == OP_LINES;
-        if (rb_op && !(p.dbg_op & OP_BYTE_PLANES) && rb_supported(32, p.R, p.K, p.flags)) {
-            RBoard<0, 0> rb(b.s, p, lane, env);
+        if (rb_op && !(p.dbg_op & OP_BYTE_PLANES) && rb_supported(32, p.R, p.K, p.flags, 0)) {
+            RBoard<0, 0, true> rb(b.s, p, lane, env);
             rb.dcur = b.dcur;
             rb.n_new = b.n_new; rb.n_act = b.n_act;
             rb.pack_from_smem();
@@ -2558,7 +2595,7 @@ template <int L> __global__ void __launch_bounds__(Cfg<L>::THREADS) k_debug(cons
                     break;
                 }
                 default: {                                   // OP_COUNT_LINES / OP_LINES
-                    const typename RBoard<0, 0>::Scan sc = rb.scan_lines();
+                    const typename RBoard<0, 0, true>::Scan sc = rb.scan_lines();
                     result = sc.rstar < 0 ? 0 : rb.build_line_table(sc);
                     to_bytes = false;
                     if (op == OP_LINES && p.dbg_out) {

@@ -33,9 +33,9 @@
 #endif
 struct RBState { uint32_t cw, tw; int n_new, n_act; uint32_t status; int aux; };
 struct RBScanPack { int rstar; unsigned mv, hs, hcells, m; int vtop, has_v; unsigned E, D, T, S; };
-template <int RT, int CT> __device__ __noinline__ RBState rb_activate_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int cell, int t, int counted);
-template <int RT, int CT> __device__ __noinline__ RBState rb_general_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, RBScanPack sc);
-template <int RT, int CT> __device__ __noinline__ RBState rb_combination_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int i1, int i2);
+template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_activate_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int cell, int t, int counted);
+template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_general_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, RBScanPack sc);
+template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_combination_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int i1, int i2);
 // words [4 b0, 4 b0 + 128) of stream 0 of env `gid` -> wbuf (one Philox block per lane); one copy per kernel
 #ifndef TMG_RB_FILL_NOINLINE
 #define TMG_RB_FILL_NOINLINE 1
@@ -47,6 +47,19 @@ template <int RT, int CT> __device__ __noinline__ RBState rb_combination_fn(RBSt
 #endif
 #ifndef TMG_RB_PROF
 #define TMG_RB_PROF 0      // per-phase cycle counters of a move (tmg_set_profile_buffer): cost 6 % even when off, so a diagnostics build only
+#endif
+// Code-size knobs.  The step kernel is bound by instruction supply and every one of these measured as throughput on B200
+// (65 536 / 1 048 576 envs, M env-steps/s): all loops unrolled and everything inline 372 / 692; refill rows rolled 375 / 702;
+// + pack / unpack rolled 385 / 748; + Philox rolled by 2, byte-plane row loops rolled 402 / 809; + the cold ends of an item
+// (playability fallback, in-step generate_board, host mirror) and the combination match out of line 416 / 833.
+#ifndef TMG_RB_ROLL_REFILL
+#define TMG_RB_ROLL_REFILL 1
+#endif
+#ifndef TMG_RB_ROLL_PACK
+#define TMG_RB_ROLL_PACK 1
+#endif
+#ifndef TMG_RB_OUTLINE_COMB
+#define TMG_RB_OUTLINE_COMB 1
 #endif
 #ifndef TMG_RB_SINGLE_FALL
 #define TMG_RB_SINGLE_FALL 1
@@ -62,7 +75,10 @@ __device__ TMG_RB_FILL_ATTR void rb_fill_words(uint32_t* wbuf, uint64_t b0, uint
     __syncwarp(0xffffffffu);
 }
 
-template <int RT, int CT> struct RBoard {
+// INJ: the instantiation can also take its draws from the injected tensor (tmg_set_injected_draws).  The step kernels
+// instantiate INJ = false only -- injected refill runs on the byte planes -- so their hot code carries no trace of it;
+// the known-answer entry point (k_debug) instantiates INJ = true.
+template <int RT, int CT, bool INJ = false> struct RBoard {
     typedef Cfg<32> CF;
     static constexpr int PS = 10;                          // plane stride: rows per bit-plane
     static constexpr uint32_t REP = 0x00100401u;           // bit 0 of every plane
@@ -158,7 +174,11 @@ template <int RT, int CT> struct RBoard {
     __device__ __forceinline__ void pack_from_smem() {
         uint32_t a = 0u, b = 0u;
         if (lane < C) {
+#if TMG_RB_ROLL_PACK
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int r = 0; r < (RT ? RT : PS); ++r) {
                 if (RT || r < R) {
                     a |= spread((int)s.board[r * C + lane]) << r;
@@ -171,7 +191,11 @@ template <int RT, int CT> struct RBoard {
     }
     __device__ __forceinline__ void unpack_to_smem() {
         if (lane < C) {
+#if TMG_RB_ROLL_PACK
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int r = 0; r < (RT ? RT : PS); ++r) {
                 if (RT || r < R) {
                     s.board[r * C + lane] = (int8_t)colour_at(r);
@@ -187,10 +211,15 @@ template <int RT, int CT> struct RBoard {
         pc_valid = true;
     }
     __device__ __forceinline__ int injected_colour(int k) {
-        const int v = injected_draw(p.inj, p.inj_len, env, (long long)dcur + k);
-        if (v < 0) { status |= ST_DRAWS_EXHAUSTED; return 1; }
-        return v;
+        if constexpr (INJ) {
+            const int v = injected_draw(p.inj, p.inj_len, env, (long long)dcur + k);
+            if (v < 0) { status |= ST_DRAWS_EXHAUSTED; return 1; }
+            return v;
+        } else {
+            return 1;
+        }
     }
+    __device__ __forceinline__ bool use_inj() const { return INJ && p.use_inj; }
 
     // ---- gravity (ref :217-229) + refill (ref :231-241) of a cascade round -----------------------------------------------------------
     // general gravity of this lane's column: every run of empty cells below a tile is closed by shifting what is above it down
@@ -237,11 +266,15 @@ template <int RT, int CT> struct RBoard {
         // the ballot of the next row is in flight while this row's word is loaded (a lone warp -- the longest cascade of
         // a launch -- pays every dependent latency in full).
         const long long rel = (long long)(dcur - 4ull * pc_b0);
-        if (!p.use_inj && pc_valid && rel >= 0 && rel + P <= 128) {
+        if (!use_inj() && pc_valid && rel >= 0 && rel + P <= 128) {
             const int off = (int)rel;
             int base = 0;
             unsigned m = m0;
+#if TMG_RB_ROLL_REFILL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int r = 0; r < RR; ++r) {                            // ref :239-241: k-th draw -> k-th empty cell, row-major
                 if (e > r) {
                     const int k = 1 + (int)__umulhi(s.wbuf[off + base + __popc(m & lt)], (uint32_t)K);
@@ -264,7 +297,7 @@ template <int RT, int CT> struct RBoard {
         for (int ps = 0; ps < total;) {
             const uint64_t start = dcur + (uint64_t)ps;
             int off = 0, nw = total - ps;
-            if (!p.use_inj) {
+            if (!use_inj()) {
                 const long long rl = (long long)(start - 4ull * pc_b0);
                 const bool inside = pc_valid && rl >= 0 && rl + nw <= 128;
                 if (!inside && !(pc_valid && rl >= 0 && rl < 4)) fill_cache(start >> 2);
@@ -278,7 +311,7 @@ template <int RT, int CT> struct RBoard {
                 if (e > r) {
                     const int rank = base + __popc(mm & lt);
                     if (rank >= ps && rank < ps + nw) {
-                        const int k = p.use_inj ? injected_colour(rank) : 1 + (int)__umulhi(s.wbuf[off + rank - ps], (uint32_t)K);
+                        const int k = use_inj() ? injected_colour(rank) : 1 + (int)__umulhi(s.wbuf[off + rank - ps], (uint32_t)K);
                         cw |= spread(k) << r;
                         tw |= 1u << r;
                     }
@@ -533,7 +566,7 @@ template <int RT, int CT> struct RBoard {
     }
     __device__ __forceinline__ void activate(int cell, int t, bool counted) {   // one call, wherever a special is hit
 #if TMG_RB_OUTLINE
-        set_state(rb_activate_fn<RT, CT>(get_state(), &p, &s, lane, env, cell, t, (int)counted));
+        set_state(rb_activate_fn<RT, CT, INJ>(get_state(), &p, &s, lane, env, cell, t, (int)counted));
 #else
         activate_impl(cell, t, counted);
 #endif
@@ -803,7 +836,7 @@ template <int RT, int CT> struct RBoard {
             sp.rstar = sc.rstar; sp.mv = sc.mv; sp.hs = sc.hs; sp.hcells = sc.hcells; sp.m = sc.m; sp.vtop = sc.vtop; sp.has_v = sc.has_v;
             sp.E = sc.bits.E; sp.D = sc.bits.D; sp.T = sc.bits.T; sp.S = sc.bits.S;
 #if TMG_RB_OUTLINE
-            const RBState st = rb_general_fn<RT, CT>(get_state(), &p, &s, lane, env, sp);
+            const RBState st = rb_general_fn<RT, CT, INJ>(get_state(), &p, &s, lane, env, sp);
             set_state(st);
             n = st.aux;
 #else
@@ -816,8 +849,8 @@ template <int RT, int CT> struct RBoard {
 
     // ---- combination_match (ref :600-719), as Board::combination -----------------------------------------------------------------------
     __device__ __forceinline__ void combination(int i1, int i2) {
-#if TMG_RB_OUTLINE
-        set_state(rb_combination_fn<RT, CT>(get_state(), &p, &s, lane, env, i1, i2));
+#if TMG_RB_OUTLINE || TMG_RB_OUTLINE_COMB
+        set_state(rb_combination_fn<RT, CT, INJ>(get_state(), &p, &s, lane, env, i1, i2));
 #else
         combination_impl(i1, i2);
 #endif
@@ -985,22 +1018,22 @@ template <int RT, int CT> struct RBoard {
     __device__ __forceinline__ int special_count() { return radd(__popc(bits_S())); }
 };
 
-template <int RT, int CT> __device__ __noinline__ RBState rb_activate_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int cell, int t, int counted) {
-    RBoard<RT, CT> b(*sm, *pp, lane, env);
+template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_activate_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int cell, int t, int counted) {
+    RBoard<RT, CT, INJ> b(*sm, *pp, lane, env);
     b.set_state(st);
     b.activate_impl(cell, t, counted != 0);
     return b.get_state();
 }
-template <int RT, int CT> __device__ __noinline__ RBState rb_general_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, RBScanPack sc) {
-    RBoard<RT, CT> b(*sm, *pp, lane, env);
+template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_general_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, RBScanPack sc) {
+    RBoard<RT, CT, INJ> b(*sm, *pp, lane, env);
     b.set_state(st);
     const int n = b.general_impl(sc);
     RBState o = b.get_state();
     o.aux = n;
     return o;
 }
-template <int RT, int CT> __device__ __noinline__ RBState rb_combination_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int i1, int i2) {
-    RBoard<RT, CT> b(*sm, *pp, lane, env);
+template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_combination_fn(RBState st, const Params* pp, GroupSmem<32>* sm, int lane, int env, int i1, int i2) {
+    RBoard<RT, CT, INJ> b(*sm, *pp, lane, env);
     b.set_state(st);
     b.combination_impl(i1, i2);
     return b.get_state();
