@@ -54,7 +54,7 @@ CONFIGS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_work launch of config 2 (ncu --set full, profiles/): no-op steps
 # never load their board and writes stay in the 126 MB L2 within a launch
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {2: 6.07e6}
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {2: 8.0e6}   # profiles/r02_kernels_ncu.txt: 7.87 MB read + 0.13 MB written
 
 
 def workload(cfg_id):

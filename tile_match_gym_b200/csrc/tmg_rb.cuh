@@ -51,7 +51,10 @@ template <int RT, int CT, bool INJ> __device__ __noinline__ RBState rb_combinati
 // Code-size knobs.  The step kernel is bound by instruction supply and every one of these measured as throughput on B200
 // (65 536 / 1 048 576 envs, M env-steps/s): all loops unrolled and everything inline 372 / 692; refill rows rolled 375 / 702;
 // + pack / unpack rolled 385 / 748; + Philox rolled by 2, byte-plane row loops rolled 402 / 809; + the cold ends of an item
-// (playability fallback, in-step generate_board, host mirror) and the combination match out of line 416 / 833.
+// (playability fallback, in-step generate_board) and the combination match out of line 416 / 833; + host mirror out of
+// line, injected refill out of this engine 440 / 935.  Not every cut pays: activate() at one call site and the cookie's
+// colour count out of line measured 432 / 910, shortcuts for single-line rounds and lone lasers / bombs (MORE code, fewer
+// executed instructions) 361 / 647 against 372 / 690 -- the kernel wants less code more than it wants fewer instructions.
 #ifndef TMG_RB_ROLL_REFILL
 #define TMG_RB_ROLL_REFILL 1
 #endif
