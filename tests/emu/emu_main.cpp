@@ -108,6 +108,7 @@ static void run_group(int L, int first_tid, void (*fn)()) {
 using namespace tmg;
 
 static Params g_params;
+static bool mir() { return g_params.h_board || g_params.h_board_packed || g_params.h_mask || g_params.h_mask_bits || g_params.h_reward; }
 static bool rbk() { return rb_supported(32, g_params.R, g_params.K, g_params.flags, g_params.use_inj); }
 template <int L> static void e_reset() {
     if (g_params.R == 10 && g_params.C == 10 && L == 32) k_reset<32, 10, 10>(g_params);
@@ -116,11 +117,11 @@ template <int L> static void e_reset() {
     else k_reset<L, 0, 0>(g_params);
 }
 template <int L> static void e_step() {
-    if (g_params.R == 10 && g_params.C == 10 && L == 32) (rbk() ? k_work<32, 10, 10, true>(g_params) : k_work<32, 10, 10, false>(g_params));
-    else if (g_params.R == 9 && g_params.C == 9 && L == 32) (rbk() ? k_work<32, 9, 9, true>(g_params) : k_work<32, 9, 9, false>(g_params));
-    else if (g_params.R == 32 && g_params.C == 32 && L == 32) k_work<32, 32, 32, false>(g_params);
-    else if (rbk() && L == 32) k_work<L, 0, 0, true>(g_params);
-    else k_work<L, 0, 0, false>(g_params);
+    if (g_params.R == 10 && g_params.C == 10 && L == 32) (rbk() ? (mir() ? k_work<32, 10, 10, true, true>(g_params) : k_work<32, 10, 10, true, false>(g_params)) : (mir() ? k_work<32, 10, 10, false, true>(g_params) : k_work<32, 10, 10, false, false>(g_params)));
+    else if (g_params.R == 9 && g_params.C == 9 && L == 32) (rbk() ? (mir() ? k_work<32, 9, 9, true, true>(g_params) : k_work<32, 9, 9, true, false>(g_params)) : (mir() ? k_work<32, 9, 9, false, true>(g_params) : k_work<32, 9, 9, false, false>(g_params)));
+    else if (g_params.R == 32 && g_params.C == 32 && L == 32) (mir() ? k_work<32, 32, 32, false, true>(g_params) : k_work<32, 32, 32, false, false>(g_params));
+    else if (rbk() && L == 32) (mir() ? k_work<L, 0, 0, true, true>(g_params) : k_work<L, 0, 0, true, false>(g_params));
+    else (mir() ? k_work<L, 0, 0, false, true>(g_params) : k_work<L, 0, 0, false, false>(g_params));
 }
 static void e_gate() { k_gate(g_params); }
 // one thread per env, whole warps (k_gate)

@@ -482,13 +482,17 @@ int tmg_step(tmg_env* e, const int32_t* actions_dev, void* stream) {
         constexpr int L = S::L;
         int grid = grid_for<L>(p.N);
         if (grid > e->persistent_blocks) grid = e->persistent_blocks;
+        const size_t smem = Cfg<L>::GPB * sizeof(GroupSmem<L>);
+        const bool mir = e->hm_bound;   // a host mirror is bound: the instantiation that writes it through inline
         if constexpr (UsesRB<L, S::R>::maybe) {   // the register-resident engine where it applies (tmg_rb.cuh)
             if (rb_supported(L, p.R, p.K, p.flags, p.use_inj)) {
-                k_work<L, S::R, S::C, true><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+                if (mir) k_work<L, S::R, S::C, true, true><<<grid, Cfg<L>::THREADS, smem, st>>>(p);
+                else k_work<L, S::R, S::C, true, false><<<grid, Cfg<L>::THREADS, smem, st>>>(p);
                 return last_error();
             }
         }
-        k_work<L, S::R, S::C, false><<<grid, Cfg<L>::THREADS, Cfg<L>::GPB * sizeof(GroupSmem<L>), st>>>(p);
+        if (mir) k_work<L, S::R, S::C, false, true><<<grid, Cfg<L>::THREADS, smem, st>>>(p);
+        else k_work<L, S::R, S::C, false, false><<<grid, Cfg<L>::THREADS, smem, st>>>(p);
         return last_error();
     });
     if (rc != TMG_OK) return rc;

@@ -2186,7 +2186,7 @@ template <int L> __device__ __forceinline__ uint32_t pop_item(const GroupCtx<L>&
 }
 
 // end of a work-list item: playability (ref board.py:381-391), the next board if the episode ended, state and outputs
-template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Board<L, RT, CT>& b, const Params& p, uint32_t packed,
+template <int L, int RT, int CT, bool MIR> __device__ __forceinline__ void finish_item(Board<L, RT, CT>& b, const Params& p, uint32_t packed,
                                                                             int elim, int is_comb, long long prof_t0,
                                                                             bool mask_ok = false, unsigned effv0 = 0u, unsigned effh0 = 0u) {
     const int lane = b.lane, env = b.env;
@@ -2227,7 +2227,28 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
             else if (dirty) { b.mask_to_smem(effv, effh); b.store_mask(); mirror |= MIRROR_MASK_SMEM; }
         }
     }
-    if ((mirrored && mirror) || (mirror & STORE_ZERO_MASK)) mirror_item<L, RT, CT>(&b.s, &p, lane, b.gmask, b.gshift, env, mirror);
+    // MIR: the instantiation that runs while a host mirror is bound writes it through inline (it is on the path of every
+    // changed env then); the other instantiation carries no mirror code at all.  The all-zero mask of a terminal step is
+    // rare either way.
+    if constexpr (MIR) {
+        if (mirror & STORE_ZERO_MASK) b.store_zero_mask();
+        if (mirror & (MIRROR_BOARD_SMEM | MIRROR_BOARD_POOL)) {
+            b.sync();
+            const int8_t* src = (mirror & MIRROR_BOARD_POOL) ? p.pool_board + (size_t)env * 2 * p.P : b.s.board;
+            if (p.h_board) b.copy_board(p.h_board + (size_t)env * 2 * p.P, src, p.board_vecw);
+            if (p.h_board_packed) b.mirror_board_packed(src);
+        }
+        if (p.h_mask || p.h_mask_bits) {
+            if (mirror & MIRROR_MASK_POOL) {
+                b.copy_mask(b.s.mask, p.pool_mask + (size_t)env * p.A);
+                b.sync();
+                b.mirror_mask(false);
+            } else if (mirror & MIRROR_MASK_SMEM) { b.sync(); b.mirror_mask(false); }
+            else if (mirror & MIRROR_MASK_ZERO) b.mirror_mask(true);
+        }
+    } else {
+        if ((mirrored && mirror) || (mirror & STORE_ZERO_MASK)) mirror_item<L, RT, CT>(&b.s, &p, lane, b.gmask, b.gshift, env, mirror);
+    }
     merge_status(b, p);
     if (dirty || from_pool) {              // scheduling hint for the next step: special tiles on the board (a fresh board has none)
         const int nsp = regenerate ? 0 : min(255, b.radd(__popc(b.last_S)));
@@ -2257,7 +2278,7 @@ template <int L, int RT, int CT> __device__ __forceinline__ void finish_item(Boa
 // special tiles), so that the longest item of the launch runs beside the bulk instead of trailing it.
 // (A warp-level state machine that aligns the cascade rounds of the warp's groups, like k_pregen's loop, was measured
 // no faster here: collectives with a group mask make the groups of a warp separate instruction streams anyway.)
-template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_work(const __grid_constant__ Params p) {
+template <int L, int RT, int CT, bool RBK, bool MIR> __global__ void __launch_bounds__(Cfg<L>::THREADS, TMG_STEP_MIN_BLOCKS) k_work(const __grid_constant__ Params p) {
     const GroupCtx<L> gc;
     if (gc.idle) return;
     const int q = p.seq & 1;
@@ -2291,7 +2312,7 @@ template <int L, int RT, int CT, bool RBK> __global__ void __launch_bounds__(Cfg
                 while (b.cascade_trip(pending_fall, elim)) {}
             }
         }
-        finish_item<L, RT, CT>(b, p, packed, elim, is_comb, prof_t0, mask_ok, effv, effh);
+        finish_item<L, RT, CT, MIR>(b, p, packed, elim, is_comb, prof_t0, mask_ok, effv, effh);
     }
 }
 
