@@ -53,6 +53,7 @@ static inline int __ffs(int x) { return x == 0 ? 0 : __builtin_ctz((unsigned)x) 
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31u)); }
 static inline long long clock64() { return 0; }
 static inline void __threadfence() {}
 template <typename T> static inline T __ldcg(const T* p) { return *p; }

@@ -1647,28 +1647,44 @@ template <int L, int RT = 0, int CT = 0> struct Board {
         in_reset = true;
         rsc = 0ull;
         uint32_t cur = 0u, row = 0u;       // reset-stream cursor (fits 32 bits: max_iters * P draws), this lane's row
+        // Window of the reset stream kept in shared memory as COLOURS: draws [wb, wend), wb a multiple of 4, 4 * L draws per
+        // Philox pass (lane j computes block wb / 4 + j).  A redraw takes on average half the board, so one pass serves about
+        // two iterations.  BITS == 2: the window is a stream of 2-bit cells (lane j stores the byte of its four cells) and a
+        // row is one funnel shift out of two words; BITS == 3: one byte per draw.
+        uint32_t wb = 0u, wend = 0u;
         int n_rows = RR, from = RR - 1;    // ref :96-97: the initial fill draws every row
         iters = 0; capped = false;
 #pragma unroll 1
         for (;;) {
             // cells [0, n_rows * C) in row-major order <- the next draws (ref :97 / :129): cell i takes word cur + i
-            const int off = (int)(cur & 3u);
-            const int nb = (off + n_rows * CC + 3) >> 2;                       // Philox blocks of this redraw, <= L
-            sync();
-            if (lane < nb) {
+            const uint32_t n = (uint32_t)(n_rows * CC);
+            if (cur + n > wend) {                                              // (cur & 3) + n <= 4 * L: one pass always suffices
+                wb = cur & ~3u;
+                wend = wb + 4u * L;
                 uint32_t w[4];
-                philox4x32_10<PHU>((cur >> 2) + (uint32_t)lane, ep, gid, 3u, p.key0, p.key1, w);
-                *reinterpret_cast<uint4*>(&s.wbuf[4 * lane]) = *reinterpret_cast<uint4*>(w);
+                philox4x32_10<PHU>((wb >> 2) + (uint32_t)lane, ep, gid, 3u, p.key0, p.key1, w);
+                const uint32_t c0 = __umulhi(w[0], (uint32_t)K), c1 = __umulhi(w[1], (uint32_t)K), c2 = __umulhi(w[2], (uint32_t)K),
+                               c3 = __umulhi(w[3], (uint32_t)K);
+                sync();
+                if (BITS == 2) reinterpret_cast<uint8_t*>(s.wbuf)[lane] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+                else s.wbuf[lane] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+                sync();
             }
-            sync();
             if (lane < n_rows) {
-                const uint32_t* wp = &s.wbuf[off + lane * CC];
-                uint32_t acc = 0u;
+                const uint32_t first = cur - wb + (uint32_t)(lane * CC);       // this row's first draw, relative to the window
+                if (BITS == 2) {
+                    constexpr uint32_t rowmask = (CC * 2 >= 32) ? 0xffffffffu : ((1u << ((CC * 2) & 31)) - 1u);
+                    const uint32_t bit = first * 2u;
+                    row = __funnelshift_r(s.wbuf[bit >> 5], s.wbuf[(bit >> 5) + 1], bit & 31u) & rowmask;
+                } else {
+                    const uint8_t* bp = reinterpret_cast<const uint8_t*>(s.wbuf) + first;
+                    uint32_t acc = 0u;
 #pragma unroll
-                for (int c = 0; c < CC; ++c) acc |= __umulhi(wp[c], (uint32_t)K) << (c * BITS);
-                row = acc;
+                    for (int c = 0; c < CC; ++c) acc |= (uint32_t)bp[c] << (c * BITS);
+                    row = acc;
+                }
             }
-            cur += (uint32_t)(n_rows * CC);
+            cur += n;
             // line scan (ref :149-196 with every tile normal): H = left ends of horizontal triples in this lane's row,
             // V = bottoms of vertical triples ending in it
             const uint32_t up1 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)row, 1), up2 = (uint32_t)__shfl_up_sync(0xffffffffu, (int)row, 2);
