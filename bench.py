@@ -498,7 +498,7 @@ def main():
     kernel_ms = total_ms / args.steps
     achieved = wl["bytes_per_step"] * n_local / (kernel_ms * 1e-3) / 1e9
     if rank == 0:
-        lib_every = max(1, min(8, num_moves // 4)) if num_moves >= 8 else 1
+        lib_every = max(1, min(4, num_moves // 4)) if num_moves >= 8 else 1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8",

@@ -317,7 +317,10 @@ int tmg_create(const tmg_config* cfg, tmg_env** out) {
     e->steps_since_pregen = 0;
     // One k_pregen launch per `pregen_every` steps: a board requested at an episode end is wanted num_moves steps later,
     // so the requests of a few steps are served together (fewer, fuller launches when the episode phases differ).
-    e->pregen_every = cfg->num_moves >= 8 ? (cfg->num_moves / 4 < 8 ? cfg->num_moves / 4 : 8) : 1;
+    // Measured (B200, config 2, staggered phases; bench 120/30, 20/5 steps at 65 536 envs, 60/10 at 1 M): every 2 steps
+    // 428 / 423 M, 3: 443 / 431 / 1021 M, 4: 444 / 447 / 1021 M, 5: 445 / 450 M, 7: 443 / 418 / 980 M, 12: 447 / 406 M -- the
+    // refill left open at the end of a run is drained inside its timed total, which is what a long interval costs a short run.
+    e->pregen_every = cfg->num_moves >= 8 ? (cfg->num_moves / 4 < 4 ? cfg->num_moves / 4 : 4) : 1;
     if (const char* pe = getenv("TMG_B200_PREGEN_EVERY")) { if (atoi(pe) > 0) e->pregen_every = atoi(pe); }
     for (int i = 0; i < tmg_env::RING; ++i) e->pregen_step[i] = 0;
     e->hm_board = nullptr; e->hm_mask = nullptr; e->hm_mask_bits = nullptr; e->hm_terminated = nullptr;
