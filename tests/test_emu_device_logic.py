@@ -270,3 +270,20 @@ def test_emulated_constructive_reset_matches_oracle(N, R, Cc, K, moves):
         assert np.array_equal(e.board, o.board) and np.array_equal(e.reward, o.reward) and np.array_equal(e.mask, o.mask), t
         assert np.array_equal(e.draw_cursor, o.draw_cursor)
     assert (e.status == 0).all() and (o.status == 0).all() and int(o.episode.max()) == 3
+
+
+@pytest.mark.parametrize("R,C,K", [(10, 10, 7), (10, 10, 8), (9, 9, 4), (9, 9, 8), (10, 10, 5)])
+def test_emulated_packed_row_generator_shapes(R, C, K):
+    """Board::generate_packed (fixed shapes, colour window of the reset stream): both cell widths (K <= 4: 2-bit stream and
+    funnel-shifted rows, K <= 8: byte window) at both row lengths, through reset, the pool and the in-step fallback."""
+    N, moves = 24, 3
+    for flags in (0, 2):                                     # 2 = TMG_FLAG_NO_PREGEN
+        e = EmuVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=11, autoreset="same_step", env_id_offset=7, flags=flags)
+        o = orc.OracleVecEnv(N, R, C, K, moves, ALL_CL, ALL_CS, seed=11, autoreset="same_step", env_id_offset=7, num_threads=4)
+        e.reset(); o.reset()
+        rng = np.random.default_rng(5)
+        for t in range(2 * moves + 1):
+            for f in ("board", "mask", "status", "episode", "draw_cursor", "shuffle_cursor"):
+                assert np.array_equal(getattr(e, f), getattr(o, f)), (flags, t, f)
+            a = rng.integers(0, o.A, N).astype(np.int32)
+            e.step(a); o.step(a)

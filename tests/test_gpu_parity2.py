@@ -418,3 +418,22 @@ def test_packed_board_host_output(mirror):
     big.reset()
     with pytest.raises(RuntimeError):
         HostStepper(big, outputs=("board_packed",), mirror=True)
+
+
+@pytest.mark.parametrize("R,Cc,K", [(10, 10, 3), (10, 10, 4), (10, 10, 5), (10, 10, 8), (9, 9, 3), (9, 9, 4), (9, 9, 6), (9, 9, 8)])
+def test_packed_row_generator_all_widths(R, Cc, K):
+    """Board::generate_packed with the colour window of the reset stream: both cell widths (K <= 4: 2-bit stream and
+    funnel-shifted rows; K <= 8: byte window) at both fixed row lengths, through tmg_reset, the pool (k_pregen) and the
+    in-step fallback (TMG_FLAG_NO_PREGEN) -- boards, masks, cursors and the iteration-cap status against the oracle."""
+    N, moves = 512, 3
+    for kw in ({}, {"pregenerate": False}):
+        g = GpuAdapter(make_gpu(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=11, autoreset="same_step", **kw))
+        o = orc.OracleVecEnv(N, R, Cc, K, moves, ALL_CL, ALL_CS, seed=11, autoreset="same_step", num_threads=os.cpu_count() or 8)
+        g.reset(); o.reset()
+        assert_same(g, o, "reset")
+        rng = np.random.default_rng(5)
+        for t in range(2 * moves + 1):
+            a = rng.integers(0, o.A, size=N).astype(np.int32)
+            g.step(a); o.step(a)
+            assert_same(g, o, f"step {t} {kw}")
+        assert int(o.episode.max()) >= 2
